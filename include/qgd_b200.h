@@ -1,0 +1,212 @@
+/*
+ * qgd_b200.h -- C ABI of the B200-native gradient hot path of QuantumGateDesign.jl.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / CUDA types.
+ * A Julia host binds these with `ccall` exactly the way the reference already binds
+ * its only native dependency (`ccall((:bsplvd_, lib), Cvoid, (Ref{Float64}, ...))`,
+ * reference src/Controls/FortranBSpline.jl:257-265).  INTEGRATION.md shows the
+ * Julia-side stub for every entry point.
+ *
+ * Conventions (all follow the reference so a Julia `Array{Float64}` can be passed as is):
+ *   - every array is column-major Float64 (or Int64 where stated), owned by the caller;
+ *   - N = N_tot_levels, 2N = real_system_size, m = order/2, nic = N_initial_conditions,
+ *     Nc = N_operators, P = total number of control coefficients;
+ *   - the state is the real-split stack w = [u; v] (reference docs/src/index.md:35-48);
+ *   - history arrays have the reference layout [2N, 1+m, 1+nsteps/save, nic]
+ *     (reference src/forward_evolution.jl:23,43), batched evaluations append a
+ *     trailing batch index;
+ *   - every function returns 0 on success, a negative QGD_E* code otherwise, never
+ *     unwinds across the boundary; the message is available from qgd_last_error().
+ *   - one call in flight per handle (the reference's callers are single threaded,
+ *     Ipopt invokes its callbacks serially, src/ipopt_optimal_control.jl:243-346).
+ */
+#ifndef QGD_B200_H
+#define QGD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QGD_OK 0
+#define QGD_EINVAL (-1)      /* bad argument (reference: ArgumentError / @assert)        */
+#define QGD_ECUDA (-2)       /* CUDA runtime failure, or no usable sm_100 device          */
+#define QGD_ENOMEM (-3)      /* device allocation failed                                  */
+#define QGD_EUNSUPPORTED (-4)/* valid in the reference but not built here */
+#define QGD_ESTATE (-5)      /* call sequence error (e.g. history_precomputed w/o history) */
+
+/* ---- operator matrices: reference SchrodingerProb{M} with M dense or SparseMatrixCSC
+ *      (src/SchrodingerProb.jl:25-41) ------------------------------------------------ */
+#define QGD_MAT_DENSE 0
+#define QGD_MAT_CSC 1
+typedef struct qgd_matrix {
+  int32_t kind;          /* QGD_MAT_DENSE | QGD_MAT_CSC                                   */
+  int32_t reserved;
+  int64_t nrows, ncols;
+  const double *dense;   /* [nrows*ncols] column-major, kind == QGD_MAT_DENSE             */
+  int64_t nnz;           /* kind == QGD_MAT_CSC: Julia SparseMatrixCSC fields, 1-based    */
+  const int64_t *colptr; /* [ncols+1]                                                     */
+  const int64_t *rowval; /* [nnz]                                                         */
+  const double *nzval;   /* [nnz]                                                         */
+} qgd_matrix_t;
+
+/* ---- controls on the hot path (reference src/Controls/) ----------- */
+#define QGD_CONTROL_GRAPE 1           /* GRAPEControl(N_amplitudes, tf)      grape_control.jl:18-26   */
+#define QGD_CONTROL_BSPLINE2 2        /* BSpline2Control(D1, tf)             bspline_control.jl:21-43 */
+#define QGD_CONTROL_FORTRAN_BSPLINE 3 /* FortranBSplineControl(degree, N_basis, tf) FortranBSpline.jl:16-61 */
+typedef struct qgd_control {
+  int32_t type;          /* base control type, QGD_CONTROL_*                              */
+  int32_t reserved;
+  double tf;
+  int64_t n_amplitudes;  /* GRAPE                                                         */
+  int64_t D1;            /* BSpline2                                                      */
+  int64_t degree;        /* FortranBSpline                                                */
+  int64_t n_basis;       /* FortranBSpline                                                */
+  int64_t n_carriers;    /* 0: bare base control; >0: CarrierControl(base, freqs) CarrierControl.jl:5-23 */
+  const double *carrier_freqs; /* [n_carriers]                                            */
+} qgd_control_t;
+
+#define QGD_PRECOND_IDENTITY 0 /* IdentityPreconditioner            preconditioners.jl:35-40  */
+#define QGD_PRECOND_LU 1       /* LUPreconditioner                  preconditioners.jl:44-55  */
+#define QGD_PRECOND_DIAGONAL 2 /* DiagonalHamiltonianPreconditioner preconditioners.jl:64-126 */
+
+/* Mirror of the fields of the reference's SchrodingerProb (src/SchrodingerProb.jl:25-41)
+ * plus the control collection that the reference passes alongside it. */
+typedef struct qgd_problem {
+  int64_t N_tot_levels;
+  int64_t N_ess_levels;
+  int64_t N_initial_conditions;
+  int64_t N_operators;
+  qgd_matrix_t system_sym;        /* K_s  [N,N]                                           */
+  qgd_matrix_t system_asym;       /* S_s  [N,N]                                           */
+  const qgd_matrix_t *sym_operators;  /* [Nc] K_c                                         */
+  const qgd_matrix_t *asym_operators; /* [Nc] S_c                                         */
+  const double *u0;               /* [N, nic]                                             */
+  const double *v0;               /* [N, nic]                                             */
+  qgd_matrix_t guard_subspace_projector; /* [2N,2N]; nnz==0 / all-zero allowed            */
+  double tf;
+  int64_t nsteps;
+  double gmres_abstol;
+  double gmres_reltol;
+  int32_t preconditioner;         /* QGD_PRECOND_*                                        */
+  int32_t reserved;
+  const qgd_control_t *controls;  /* [Nc], control k drives operator k                    */
+} qgd_problem_t;
+
+typedef struct qgd_handle qgd_handle_t;
+
+/* Number of coefficients of one control / of the whole collection
+ * (reference get_number_of_control_parameters, src/Controls/Control.jl:94-96). */
+int64_t qgd_control_n_coeff(const qgd_control_t *c);
+int64_t qgd_problem_n_coeff(const qgd_problem_t *p);
+
+/* Build the device-resident problem: validates like the reference's inner constructor
+ * (symmetry / antisymmetry / shapes, src/SchrodingerProb.jl:73-154), converts the
+ * operators to the on-chip row format, builds the preconditioner factors. `device` is the
+ * CUDA ordinal (-1: current device). Fails with QGD_ECUDA when no sm_100 GPU is present;
+ * there is no CPU fallback. */
+int qgd_create(const qgd_problem_t *prob, int device, qgd_handle_t **out);
+int qgd_destroy(qgd_handle_t *h);
+const char *qgd_last_error(void);
+
+/* The reference mutates prob.nsteps / prob.gmres_abstol / prob.gmres_reltol in place
+ * (examples/cnot3_optimize_gate.jl:51-55); the same three knobs here. */
+int qgd_set_nsteps(qgd_handle_t *h, int64_t nsteps);
+int qgd_set_gmres_tolerances(qgd_handle_t *h, double abstol, double reltol);
+
+/* Restrict this handle to the initial-condition columns [col_begin, col_begin+col_count)
+ * (multi-GPU column sharding: one process per GPU each owning a contiguous block, the
+ * GPU counterpart of `Threads.@threads for initial_condition_index`,
+ * src/forward_evolution.jl:48,332).  Default: all columns. */
+int qgd_set_column_shard(qgd_handle_t *h, int64_t col_begin, int64_t col_count);
+
+/* eval_forward! (src/forward_evolution.jl:33-70, 88-245) for n_batch control vectors.
+ *   pcof        [P, n_batch]
+ *   history     [2N, 1+m, 1+nsteps/save_every, ncol, n_batch]  or NULL (kept on device only)
+ *   final_state [2N, ncol, n_batch] or NULL            (history[:,1,end,:])
+ *   gmres_iters [nsteps, ncol, n_batch] Int64 or NULL  (loop count of :211-217 per step)
+ * ncol = columns owned by this handle. */
+int qgd_eval_forward(qgd_handle_t *h, const double *pcof, int64_t n_batch, int32_t order,
+                     int64_t save_every, double *history, double *final_state,
+                     int64_t *gmres_iters);
+
+/* discrete_adjoint! (src/eval_grad_discrete_adjoint.jl:107-160), cost_type = :Infidelity.
+ *   target      [2N, nic] real-stacked vcat(real, imag) of the complex gate (what
+ *               complex_to_real produces at :126); ALL nic columns even when sharded
+ *   history_precomputed != 0: reuse the history left on the device by the previous
+ *               qgd_eval_forward / qgd_discrete_adjoint call of this handle (same pcof batch)
+ *   grad        [P, n_batch]                         (sum over this handle's columns)
+ *   infidelity  [n_batch]  infidelity_real (src/infidelity.jl:7-18)   (all columns needed:
+ *               in sharded mode use the two-phase API below)
+ *   guard_penalty [n_batch] guard_penalty_real (src/infidelity.jl:56-96)
+ *   history, lambda_history [2N,1+m,1+nsteps,ncol,n_batch] or NULL
+ *   adjoint_forcing [2N,1+nsteps,ncol,n_batch] or NULL
+ *   iters_fwd, iters_adj [nsteps, ncol, n_batch] or NULL; iters_term [nic, n_batch] or NULL */
+int qgd_discrete_adjoint(qgd_handle_t *h, const double *pcof, int64_t n_batch,
+                         const double *target, int32_t order, int32_t history_precomputed,
+                         double *grad, double *infidelity, double *guard_penalty,
+                         double *history, double *lambda_history, double *adjoint_forcing,
+                         int64_t *iters_fwd, int64_t *iters_adj, int64_t *iters_term);
+
+/* Same evaluation with every buffer already in device memory (HBM) and nothing copied:
+ * d_pcof [P,n_batch], d_target [2N,nic], d_grad [P,n_batch], d_infidelity/d_guard [n_batch].
+ * Launches on `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream) and
+ * returns without synchronising. */
+int qgd_discrete_adjoint_device(qgd_handle_t *h, const double *d_pcof, int64_t n_batch,
+                                const double *d_target, int32_t order, double *d_grad,
+                                double *d_infidelity, double *d_guard_penalty, void *stream);
+
+/* Two-phase form for column sharding across GPUs: phase 1 runs the forward
+ * sweep on the owned columns and returns their final states and guard-penalty partial;
+ * the host all-gathers the final states (the only cross-column coupling: <psi,R>, <psi,T>
+ * of compute_terminal_condition, src/eval_grad_discrete_adjoint.jl:27-28); phase 2 takes
+ * the final states of ALL columns and produces this rank's gradient partial, to be
+ * all-reduced by the host.
+ *   final_state_local [2N, ncol, n_batch], guard_local [n_batch]
+ *   final_state_all   [2N, nic, n_batch] */
+int qgd_adjoint_phase1(qgd_handle_t *h, const double *pcof, int64_t n_batch, int32_t order,
+                       double *final_state_local, double *guard_local);
+int qgd_adjoint_phase2(qgd_handle_t *h, const double *target, const double *final_state_all,
+                       double *grad_local, double *infidelity);
+
+/* Objective pieces on their own (src/infidelity.jl:7-18, 56-96). final_state [2N,nic,n_batch]. */
+int qgd_infidelity_real(qgd_handle_t *h, const double *final_state, const double *target,
+                        int64_t n_batch, double *infidelity);
+
+/* Control evaluation, kernel K1 (fill_p_mat!/fill_q_mat!, src/Controls/Control.jl:125-149):
+ *   times [ntimes]; pcof [P]; p_out,q_out [nderiv, Nc, ntimes] with entry (1+j,k,it) =
+ *   p_k^(j)(t)/j!  -- the Taylor-scaled values the time stepper consumes.
+ * grad tables (eval_grad_{p,q}_derivative!, e.g. FortranBSpline.jl:149-189), un-scaled:
+ *   gp_out,gq_out [P, nderiv, ntimes] with entry (theta, 1+r, it) = d p_k(theta)^(r)(t) / d theta
+ *   where k(theta) is the control owning coefficient theta; either may be NULL. */
+int qgd_eval_controls(qgd_handle_t *h, const double *pcof, const double *times, int64_t ntimes,
+                      int32_t nderiv, double *p_out, double *q_out, double *gp_out,
+                      double *gq_out);
+
+/* Kernel K2 on its own (compute_derivatives!, src/hermite.jl:56-101 and the transposed
+ * recursion W_j(t)^T x of compute_adjoint_derivatives!, :284-305):
+ *   uv [2N, 1+m, ncols_in]: column 1 given, columns 2..1+m overwritten;
+ *   cvals_re, cvals_im [1+m, Nc]; adjoint != 0 selects Lambda_j = W_j^T x. */
+int qgd_compute_derivatives(qgd_handle_t *h, double *uv, int64_t ncols_in, int32_t order,
+                            const double *cvals_re, const double *cvals_im, int32_t adjoint);
+
+/* Counters of the last call, for tracing: kernel launches, bytes copied each way. */
+typedef struct qgd_stats {
+  int64_t kernel_launches;
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  double last_forward_ms;  /* CUDA-event time of the forward sweep kernel  */
+  double last_backward_ms; /* CUDA-event time of the backward sweep kernel */
+  double last_total_ms;    /* CUDA-event time of the whole device section  */
+} qgd_stats_t;
+int qgd_get_stats(qgd_handle_t *h, qgd_stats_t *out);
+
+/* Measured FP64 FMA throughput of this device in TFLOP/s (micro-benchmark kernel); the
+ * roofline denominator MEASURED_PEAKS.json does not provide. */
+int qgd_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGD_B200_H */

@@ -1,0 +1,15 @@
+"""quantumgatedesign.jl_b200 -- B200-native gradient hot path of QuantumGateDesign.jl.
+
+Host-side mirror of the reference's API for the path (SchrodingerProb, the control types,
+eval_forward, discrete_adjoint, infidelity ...) over the C ABI of csrc/libqgd_b200.so
+(include/qgd_b200.h).  The directory name contains a dot, so the package is loaded through
+`__graft_entry__.load_package()` under the module name `qgd_b200`.
+"""
+from . import _abi
+from . import configs
+from .controls import (AbstractControl, BSpline2Control, CarrierControl, FortranBSplineControl, GRAPEControl,
+                       as_control_list, control_slices, get_number_of_control_parameters)
+from .problem import (DiagonalHamiltonianPreconditioner, DispersiveProblem, IdentityPreconditioner, LUPreconditioner,
+                      SchrodingerProb, complex_to_real, construct_rabi_prob, construct_rand_prob, control_ops,
+                      create_gate, create_initial_conditions, guard_projector, lowering_operators_system,
+                      multi_qudit_hamiltonian_dispersive, real_to_complex)
