@@ -1,0 +1,259 @@
+"""ctypes binding of csrc/libqgd_b200.so (include/qgd_b200.h).
+
+The CUDA library is the only compute path: if it is missing or cannot create a handle (no sm_100
+GPU) every call raises -- there is no CPU fallback and nothing here imports the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import _abi
+from ._abi import c_double_p, c_int64_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libqgd_b200.so")
+_LIB = None
+
+EXPORTS = [
+    "qgd_last_error", "qgd_control_n_coeff", "qgd_problem_n_coeff", "qgd_create", "qgd_destroy", "qgd_set_nsteps",
+    "qgd_set_gmres_tolerances", "qgd_set_column_shard", "qgd_eval_forward", "qgd_discrete_adjoint",
+    "qgd_discrete_adjoint_device", "qgd_adjoint_phase1", "qgd_adjoint_phase2", "qgd_infidelity_real",
+    "qgd_eval_controls", "qgd_compute_derivatives", "qgd_get_stats", "qgd_measure_fp64_peak",
+]
+
+
+class QGDError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"qgd_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(jobs: int = 8, force: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, f"-j{jobs}"]
+    if force:
+        cmd.append("-B")
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise QGDError(-2, f"{LIB_PATH} is missing: run __graft_entry__.build() (the CUDA extension is the only "
+                               "compute path; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.qgd_last_error.restype = C.c_char_p
+        L.qgd_control_n_coeff.restype = C.c_int64
+        L.qgd_problem_n_coeff.restype = C.c_int64
+        L.qgd_create.argtypes = [C.POINTER(_abi.qgd_problem_t), C.c_int, C.POINTER(C.c_void_p)]
+        L.qgd_destroy.argtypes = [C.c_void_p]
+        L.qgd_set_nsteps.argtypes = [C.c_void_p, C.c_int64]
+        L.qgd_set_gmres_tolerances.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.qgd_set_column_shard.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.qgd_eval_forward.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int32, C.c_int64, c_double_p, c_double_p,
+                                       c_int64_p]
+        L.qgd_discrete_adjoint.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, C.c_int32, C.c_int32, c_double_p,
+                                           c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int64_p,
+                                           c_int64_p, c_int64_p]
+        L.qgd_discrete_adjoint_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qgd_adjoint_phase1.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int32, c_double_p, c_double_p]
+        L.qgd_adjoint_phase2.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]
+        L.qgd_infidelity_real.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p]
+        L.qgd_eval_controls.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int32, c_double_p, c_double_p,
+                                        c_double_p, c_double_p]
+        L.qgd_compute_derivatives.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int32, c_double_p, c_double_p,
+                                              C.c_int32]
+        L.qgd_get_stats.argtypes = [C.c_void_p, C.POINTER(_abi.qgd_stats_t)]
+        L.qgd_measure_fp64_peak.argtypes = [C.c_int, c_double_p]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise QGDError(rc, lib().qgd_last_error().decode())
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_int64_p)
+
+
+def measure_fp64_peak(device: int = -1) -> float:
+    out = np.zeros(1)
+    _check(lib().qgd_measure_fp64_peak(device, _dp(out)))
+    return float(out[0])
+
+
+class Handle:
+    """Device-resident problem (qgd_handle_t).  One call in flight per handle."""
+
+    def __init__(self, prob, controls, device: int = -1):
+        self._pack = _abi.ProblemPack(prob, controls)
+        self._h = C.c_void_p()
+        _check(lib().qgd_create(self._pack.ref(), int(device), C.byref(self._h)))
+        self.N2 = prob.real_system_size
+        self.nic = prob.N_initial_conditions
+        self.ncol = self.nic
+        self.col0 = 0
+        self.nsteps = prob.nsteps
+        self.P = self._pack.n_coeff
+        self.Nc = prob.N_operators
+        self.key = problem_key(prob, controls)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().qgd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- mutable knobs of the reference's SchrodingerProb
+    def set_nsteps(self, nsteps):
+        _check(lib().qgd_set_nsteps(self._h, int(nsteps)))
+        self.nsteps = int(nsteps)
+
+    def set_gmres_tolerances(self, abstol, reltol):
+        _check(lib().qgd_set_gmres_tolerances(self._h, float(abstol), float(reltol)))
+
+    def set_column_shard(self, col_begin, col_count):
+        _check(lib().qgd_set_column_shard(self._h, int(col_begin), int(col_count)))
+        self.col0, self.ncol = int(col_begin), int(col_count)
+
+    @staticmethod
+    def _pcof(pcof, P):
+        pc = np.asarray(pcof, dtype=np.float64)
+        if pc.ndim == 1:
+            pc = pc[:, None]
+        if pc.shape[0] != P:
+            raise ValueError(f"pcof has {pc.shape[0]} coefficients, the controls need {P}")
+        return np.asfortranarray(pc)
+
+    def eval_forward(self, pcof, order=2, save_every=1, want_history=True, want_iters=True):
+        pc = self._pcof(pcof, self.P)
+        B, m = pc.shape[1], order // 2
+        nslots = 1 + self.nsteps // save_every
+        hist = np.zeros((self.N2, 1 + m, nslots, self.ncol, B), order="F") if want_history else None
+        final = np.zeros((self.N2, self.ncol, B), order="F")
+        iters = np.zeros((self.nsteps, self.ncol, B), dtype=np.int64, order="F") if want_iters else None
+        _check(lib().qgd_eval_forward(self._h, _dp(pc), B, int(order), int(save_every), _dp(hist), _dp(final), _ip(iters)))
+        return dict(history=hist, final_state=final, iters=iters)
+
+    def discrete_adjoint(self, pcof, target_real, order=2, history_precomputed=False, want_history=False,
+                         want_lambda=False, want_forcing=False, want_iters=False):
+        pc = self._pcof(pcof, self.P)
+        B, m, Nt = pc.shape[1], order // 2, self.nsteps + 1
+        tgt = np.asfortranarray(target_real, dtype=np.float64)
+        if tgt.shape != (self.N2, self.nic):
+            raise ValueError(f"target must be the real-stacked [2N, nic] = {(self.N2, self.nic)} array, got {tgt.shape}")
+        grad = np.zeros((self.P, B), order="F")
+        infid = np.zeros(B)
+        guard = np.zeros(B)
+        hist = np.zeros((self.N2, 1 + m, Nt, self.ncol, B), order="F") if want_history else None
+        lam = np.zeros((self.N2, 1 + m, Nt, self.ncol, B), order="F") if want_lambda else None
+        forc = np.zeros((self.N2, Nt, self.ncol, B), order="F") if want_forcing else None
+        itf = np.zeros((self.nsteps, self.ncol, B), dtype=np.int64, order="F") if want_iters else None
+        ita = np.zeros((self.nsteps, self.ncol, B), dtype=np.int64, order="F") if want_iters else None
+        itt = np.zeros((self.nic, B), dtype=np.int64, order="F") if want_iters else None
+        _check(lib().qgd_discrete_adjoint(self._h, _dp(pc), B, _dp(tgt), int(order), int(bool(history_precomputed)),
+                                          _dp(grad), _dp(infid), _dp(guard), _dp(hist), _dp(lam), _dp(forc), _ip(itf),
+                                          _ip(ita), _ip(itt)))
+        return dict(grad=grad, infidelity=infid, guard_penalty=guard, history=hist, lambda_history=lam,
+                    adjoint_forcing=forc, iters_fwd=itf, iters_adj=ita, iters_term=itt)
+
+    def discrete_adjoint_device(self, d_pcof_ptr, n_batch, d_target_ptr, order, d_grad_ptr, d_infid_ptr, d_guard_ptr,
+                                stream_ptr=None):
+        """Everything already in HBM (raw device pointers as ints); asynchronous on `stream_ptr`."""
+        _check(lib().qgd_discrete_adjoint_device(self._h, C.c_void_p(d_pcof_ptr), int(n_batch), C.c_void_p(d_target_ptr),
+                                                 int(order), C.c_void_p(d_grad_ptr), C.c_void_p(d_infid_ptr),
+                                                 C.c_void_p(d_guard_ptr), C.c_void_p(stream_ptr or 0)))
+
+    def adjoint_phase1(self, pcof, order):
+        pc = self._pcof(pcof, self.P)
+        B = pc.shape[1]
+        final = np.zeros((self.N2, self.ncol, B), order="F")
+        guard = np.zeros(B)
+        _check(lib().qgd_adjoint_phase1(self._h, _dp(pc), B, int(order), _dp(final), _dp(guard)))
+        return final, guard
+
+    def adjoint_phase2(self, target_real, final_all):
+        tgt = np.asfortranarray(target_real, dtype=np.float64)
+        fa = np.asfortranarray(final_all, dtype=np.float64)
+        B = fa.shape[2]
+        grad = np.zeros((self.P, B), order="F")
+        infid = np.zeros(B)
+        _check(lib().qgd_adjoint_phase2(self._h, _dp(tgt), _dp(fa), _dp(grad), _dp(infid)))
+        return grad, infid
+
+    def eval_controls(self, pcof, times, nderiv, want_grad=False):
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        pc = np.ascontiguousarray(pcof, dtype=np.float64)
+        nt = times.size
+        p = np.zeros((nderiv, self.Nc, nt), order="F")
+        q = np.zeros((nderiv, self.Nc, nt), order="F")
+        gp = np.zeros((self.P, nderiv, nt), order="F") if want_grad else None
+        gq = np.zeros((self.P, nderiv, nt), order="F") if want_grad else None
+        _check(lib().qgd_eval_controls(self._h, _dp(pc), _dp(times), nt, int(nderiv), _dp(p), _dp(q), _dp(gp), _dp(gq)))
+        return p, q, gp, gq
+
+    def compute_derivatives(self, uv, order, cre, cim, adjoint=False):
+        uv = np.asfortranarray(uv, dtype=np.float64).copy(order="F")
+        if uv.ndim == 2:
+            uv = uv[:, :, None]
+        cre = np.asfortranarray(cre, dtype=np.float64)
+        cim = np.asfortranarray(cim, dtype=np.float64)
+        _check(lib().qgd_compute_derivatives(self._h, _dp(uv), uv.shape[2], int(order), _dp(cre), _dp(cim), int(adjoint)))
+        return uv
+
+    def stats(self):
+        s = _abi.qgd_stats_t()
+        _check(lib().qgd_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in _abi.qgd_stats_t._fields_}
+
+
+def problem_key(prob, controls):
+    """Identity of the immutable parts of (prob, controls); nsteps / tolerances are mutable knobs."""
+    from .controls import as_control_list
+
+    return (id(prob), tuple(id(c) for c in as_control_list(controls)), prob.preconditioner_type, prob.tf)
+
+
+_HANDLES = {}
+
+
+def get_handle(prob, controls, device: int = -1) -> Handle:
+    """Cached device handle for (prob, controls); follows the reference's in-place mutation of
+    prob.nsteps / prob.gmres_abstol / prob.gmres_reltol (examples/cnot3_optimize_gate.jl:51-55)."""
+    key = (problem_key(prob, controls), device)
+    h = _HANDLES.get(key)
+    if h is None:
+        h = Handle(prob, controls, device)
+        h._tol = (prob.gmres_abstol, prob.gmres_reltol)
+        _HANDLES[key] = h
+    if h.nsteps != prob.nsteps:
+        h.set_nsteps(prob.nsteps)
+    if h._tol != (prob.gmres_abstol, prob.gmres_reltol):
+        h.set_gmres_tolerances(prob.gmres_abstol, prob.gmres_reltol)
+        h._tol = (prob.gmres_abstol, prob.gmres_reltol)
+    return h
+
+
+def clear_handles():
+    for h in _HANDLES.values():
+        h.close()
+    _HANDLES.clear()

@@ -1,0 +1,877 @@
+// qgd_b200.cu -- host layer + C ABI (include/qgd_b200.h) of the B200-native gradient hot path.
+// Standalone CUDA-runtime code: no torch, no CPU fallback.  Every entry point fails with QGD_ECUDA
+// when no sm_100 device is available.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/qgd_b200.h"
+#include "qgd_host.h"
+#include "qgd_controls.cuh"
+#include "qgd_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+// ---- small dense helpers (host-side setup only) --------------------------------------------------------
+dvec mat_to_dense(const qgd_matrix_t& a) {
+  dvec d((size_t)a.nrows * a.ncols, 0.0);
+  if (a.kind == QGD_MAT_CSC) {
+    for (int64_t j = 0; j < a.ncols; ++j)
+      for (int64_t p = a.colptr[j] - 1; p < a.colptr[j + 1] - 1; ++p) d[(size_t)(a.rowval[p] - 1) + a.nrows * j] += a.nzval[p];
+  } else if (a.kind == QGD_MAT_DENSE) {
+    std::copy(a.dense, a.dense + (size_t)a.nrows * a.ncols, d.begin());
+  } else {
+    throw QgdError(QGD_EINVAL, "unknown matrix kind");
+  }
+  return d;
+}
+dvec matmul(const dvec& A, const dvec& B, int n) {
+  dvec C((size_t)n * n, 0.0);
+  for (int j = 0; j < n; ++j)
+    for (int k = 0; k < n; ++k) {
+      double b = B[k + (size_t)n * j];
+      if (b == 0.0) continue;
+      for (int i = 0; i < n; ++i) C[i + (size_t)n * j] += A[i + (size_t)n * k] * b;
+    }
+  return C;
+}
+dvec matpow(const dvec& A, int p, int n) {  // Julia's A^p (Base.power_by_squaring)
+  auto tz = [](int v) { int c = 0; while (!(v & 1)) { v >>= 1; ++c; } return c; };
+  dvec x = A;
+  int t = tz(p) + 1; p >>= t;
+  while ((t -= 1) > 0) x = matmul(x, x, n);
+  dvec y = x;
+  while (p > 0) {
+    t = tz(p) + 1; p >>= t;
+    while ((t -= 1) >= 0) x = matmul(x, x, n);
+    y = matmul(y, x, n);
+  }
+  return y;
+}
+double factorial_d(int n) { double f = 1; for (int i = 2; i <= n; ++i) f *= i; return f; }
+double ipow(double x, int p) { double r = 1, b = x; while (p > 0) { if (p & 1) r *= b; p >>= 1; if (p) b *= b; } return r; }
+double coefficient(int j, int p, int q) {  // src/hermite.jl:389-391
+  return factorial_d(p) * factorial_d(p + q - j) / (factorial_d(p + q) * factorial_d(p - j));
+}
+
+int align16(int x) { return (x + 15) & ~15; }
+
+}  // namespace
+
+namespace qgd {
+
+// grad[b][theta] = sum over owned columns (fixed order); guard[b] likewise.
+__global__ void k_finalize(int P, int ncol, int B, const double* gradcol, const double* guardcol, double* grad, double* guard) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (size_t)P * B) {
+    const int b = (int)(idx / P), t = (int)(idx % P);
+    double s = 0.0;
+    for (int cl = 0; cl < ncol; ++cl) s += gradcol[(size_t)t + (size_t)P * ((size_t)cl + (size_t)ncol * b)];
+    grad[idx] = s;
+  }
+  if (guard && idx < (size_t)B) {
+    double s = 0.0;
+    for (int cl = 0; cl < ncol; ++cl) s += guardcol[(size_t)cl + (size_t)ncol * idx];
+    guard[idx] = s;
+  }
+}
+
+// FP64 FMA throughput micro-benchmark (roofline denominator MEASURED_PEAKS.json does not carry).
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
+  const double m = 0.999999999, c = 1e-12;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace qgd
+
+namespace {
+
+using namespace qgd;
+
+int pick_el(int N) {
+  int el = 1;
+  while (32 * el < N) el *= 2;
+  if (el > 4) throw QgdError(QGD_EUNSUPPORTED, "N_tot_levels > 128 is not supported by the warp-per-column kernels yet (dense large-N path: see DESIGN.md)");
+  return el;
+}
+
+void validate_and_load(qgd_handle* h, const qgd_problem_t* p) {
+  if (!p) throw QgdError(QGD_EINVAL, "null problem");
+  const int64_t N = p->N_tot_levels;
+  if (N < 1) throw QgdError(QGD_EINVAL, "N_tot_levels must be positive");
+  if (p->N_operators < 0 || p->N_operators > QGD_MAX_OPS - 1) throw QgdError(QGD_EUNSUPPORTED, "at most 8 control operators are supported");
+  if (p->N_initial_conditions < 1) throw QgdError(QGD_EINVAL, "need at least one initial condition column");
+  if (p->N_ess_levels > N) throw QgdError(QGD_EINVAL, "Number of essential levels cannot be greater than the total number of levels.");
+  if (p->nsteps < 1) throw QgdError(QGD_EINVAL, "nsteps must be >= 1");
+  if (!(p->tf > 0)) throw QgdError(QGD_EINVAL, "tf must be positive");
+  auto check_sq = [&](const qgd_matrix_t& a, int64_t n, const char* what) {
+    if (a.nrows != n || a.ncols != n) throw QgdError(QGD_EINVAL, std::string("Size of ") + what + " does not match the size of the system Hamiltonian.");
+  };
+  check_sq(p->system_sym, N, "real part of the system Hamiltonian");
+  check_sq(p->system_asym, N, "imaginary part of the system Hamiltonian");
+  check_sq(p->guard_subspace_projector, 2 * N, "guard subspace projector (should be twice the complex system size)");
+  h->N = (int)N; h->N2 = 2 * (int)N; h->Nc = (int)p->N_operators; h->nic = (int)p->N_initial_conditions; h->Ness = (int)p->N_ess_levels;
+  h->nsteps = p->nsteps; h->tf = p->tf; h->abstol = p->gmres_abstol; h->reltol = p->gmres_reltol; h->precond = p->preconditioner;
+  if (h->precond < 0 || h->precond > 2) throw QgdError(QGD_EINVAL, "preconditioner_type is not an AbstractQGDPreconditioner.");
+  h->col0 = 0; h->ncol = h->nic;
+  pick_el(h->N);
+
+  // dense copies + symmetry checks (src/SchrodingerProb.jl:73-91)
+  const int n = h->N;
+  h->Ks = mat_to_dense(p->system_sym);
+  h->Ss = mat_to_dense(p->system_asym);
+  std::vector<dvec> Kc(h->Nc), Sc(h->Nc);
+  auto is_sym = [&](const dvec& A, double sign) {
+    for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) if (A[i + (size_t)n * j] != sign * A[j + (size_t)n * i]) return false;
+    return true;
+  };
+  if (!is_sym(h->Ks, 1.0)) throw QgdError(QGD_EINVAL, "Real part of system Hamiltonian is not symmetric.");
+  if (!is_sym(h->Ss, -1.0)) throw QgdError(QGD_EINVAL, "Imaginary part of system Hamiltonian is not anti-symmetric.");
+  for (int k = 0; k < h->Nc; ++k) {
+    check_sq(p->sym_operators[k], N, "a symmetric operator");
+    check_sq(p->asym_operators[k], N, "an anti-symmetric operator");
+    Kc[k] = mat_to_dense(p->sym_operators[k]);
+    Sc[k] = mat_to_dense(p->asym_operators[k]);
+    if (!is_sym(Kc[k], 1.0)) throw QgdError(QGD_EINVAL, "Symmetric operator " + std::to_string(k + 1) + " is not symmetric.");
+    if (!is_sym(Sc[k], -1.0)) throw QgdError(QGD_EINVAL, "Anti-symmetric operator " + std::to_string(k + 1) + " is not anti-symmetric.");
+  }
+  dvec W = mat_to_dense(p->guard_subspace_projector);
+
+  // ---- controls
+  h->ctrls.resize(h->Nc); h->ctrl_freqs.resize(h->Nc); h->ctrl_knots.resize(h->Nc);
+  int off = 0;
+  for (int k = 0; k < h->Nc; ++k) {
+    const qgd_control_t& c = p->controls[k];
+    QgdDevControl dc{};
+    dc.type = c.type; dc.tf = c.tf; dc.n_carriers = (int)std::max<int64_t>(c.n_carriers, 0);
+    dc.n_amp = (int)c.n_amplitudes; dc.D1 = (int)c.D1; dc.degree = (int)c.degree; dc.n_basis = (int)c.n_basis;
+    if (c.type == QGD_CONTROL_GRAPE) {
+      if (c.n_amplitudes < 1) throw QgdError(QGD_EINVAL, "GRAPEControl: N_amplitudes must be >= 1");
+      dc.base_ncoeff = 2 * dc.n_amp;
+    } else if (c.type == QGD_CONTROL_BSPLINE2) {
+      if (c.D1 < 3) throw QgdError(QGD_EINVAL, "Number of coefficients per spline (D1) must be >= 3.");
+      dc.base_ncoeff = 2 * dc.D1;
+      dc.dtknot = c.tf / (double)(c.D1 - 2);
+    } else if (c.type == QGD_CONTROL_FORTRAN_BSPLINE) {
+      dc.order = dc.degree + 1;
+      dc.N_knots = dc.n_basis + dc.order;
+      dc.N_distinct = dc.N_knots - 2 * (dc.order - 1);
+      if (dc.N_distinct < 2) throw QgdError(QGD_EINVAL, "FortranBSplineControl: too few basis functions for this degree.");
+      if (dc.order > QGD_FBS_MAXORDER) throw QgdError(QGD_EINVAL, "FortranBSplineControl: pppack supports order <= 20 (bsplvb.f jmax).");
+      dc.base_ncoeff = 2 * dc.n_basis;
+      dvec& kn = h->ctrl_knots[k];
+      for (int i = 0; i < dc.order - 1; ++i) kn.push_back(0.0);
+      for (int i = 0; i < dc.N_distinct; ++i) kn.push_back((double)i / (double)(dc.N_distinct - 1));
+      for (int i = 0; i < dc.order - 1; ++i) kn.push_back(1.0);
+    } else {
+      throw QgdError(QGD_EUNSUPPORTED, "control type is not on the B200 hot path (GRAPE, BSpline2, FortranBSpline, Carrier)");
+    }
+    if (dc.n_carriers > 0) h->ctrl_freqs[k].assign(c.carrier_freqs, c.carrier_freqs + dc.n_carriers);
+    dc.ncoeff = dc.n_carriers > 0 ? dc.base_ncoeff * dc.n_carriers : dc.base_ncoeff;
+    dc.offset = off;
+    off += dc.ncoeff;
+    h->ctrls[k] = dc;
+  }
+  h->P = off;
+
+  // ---- operator blob: per-operator row-ELL over the union pattern of (K, S)
+  QgdOpLayout& L = h->lay;
+  std::memset(&L, 0, sizeof(L));
+  L.n_ops = h->Nc + 1;
+  std::vector<std::vector<std::vector<int>>> cols(L.n_ops);  // [op][row] -> columns
+  for (int k = 0; k < L.n_ops; ++k) {
+    const dvec& K = (k == 0) ? h->Ks : Kc[k - 1];
+    const dvec& S = (k == 0) ? h->Ss : Sc[k - 1];
+    cols[k].resize(n);
+    int Lk = 0;
+    for (int r = 0; r < n; ++r) {
+      for (int c = 0; c < n; ++c)
+        if (K[r + (size_t)n * c] != 0.0 || S[r + (size_t)n * c] != 0.0) cols[k][r].push_back(c);
+      Lk = std::max(Lk, (int)cols[k][r].size());
+    }
+    L.L[k] = Lk;
+  }
+  int pos = 0;
+  for (int k = 0; k < L.n_ops; ++k) {
+    L.off_col[k] = pos; pos = align16(pos + L.L[k] * n * 4);
+    L.off_vk[k] = pos; pos = align16(pos + L.L[k] * n * 8);
+    L.off_vs[k] = pos; pos = align16(pos + L.L[k] * n * 8);
+  }
+  const int n2 = h->N2;
+  std::vector<std::vector<int>> wcols(n2);
+  int LW = 0;
+  for (int r = 0; r < n2; ++r) {
+    for (int c = 0; c < n2; ++c) if (W[r + (size_t)n2 * c] != 0.0) wcols[r].push_back(c);
+    LW = std::max(LW, (int)wcols[r].size());
+  }
+  L.LW = LW;
+  L.off_wcol = pos; pos = align16(pos + LW * n2 * 4);
+  L.off_wval = pos; pos = align16(pos + LW * n2 * 8);
+  for (int dir = 0; dir < 2; ++dir) { L.off_pre[dir] = pos; pos = align16(pos + (n2 + 3 * n) * 8); }
+  L.bytes = align16(pos);
+  h->blob.assign(L.bytes, 0);
+  for (int k = 0; k < L.n_ops; ++k) {
+    const dvec& K = (k == 0) ? h->Ks : Kc[k - 1];
+    const dvec& S = (k == 0) ? h->Ss : Sc[k - 1];
+    int* col = reinterpret_cast<int*>(h->blob.data() + L.off_col[k]);
+    double* vk = reinterpret_cast<double*>(h->blob.data() + L.off_vk[k]);
+    double* vs = reinterpret_cast<double*>(h->blob.data() + L.off_vs[k]);
+    for (int r = 0; r < n; ++r)
+      for (int s = 0; s < L.L[k]; ++s) {
+        if (s < (int)cols[k][r].size()) {
+          int c = cols[k][r][s];
+          col[s * n + r] = c; vk[s * n + r] = K[r + (size_t)n * c]; vs[s * n + r] = S[r + (size_t)n * c];
+        } else {
+          col[s * n + r] = r; vk[s * n + r] = 0.0; vs[s * n + r] = 0.0;
+        }
+      }
+  }
+  {
+    int* col = reinterpret_cast<int*>(h->blob.data() + L.off_wcol);
+    double* val = reinterpret_cast<double*>(h->blob.data() + L.off_wval);
+    for (int r = 0; r < n2; ++r)
+      for (int s = 0; s < LW; ++s) {
+        if (s < (int)wcols[r].size()) { col[s * n2 + r] = wcols[r][s]; val[s * n2 + r] = W[r + (size_t)n2 * wcols[r][s]]; }
+        else { col[s * n2 + r] = r; val[s * n2 + r] = 0.0; }
+      }
+  }
+
+  // ---- upload the static parts
+  h->d_u0.reserve((size_t)n * h->nic * 8); h->d_v0.reserve((size_t)n * h->nic * 8);
+  CUDA_CHECK(cudaMemcpy(h->d_u0.p, p->u0, (size_t)n * h->nic * 8, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(h->d_v0.p, p->v0, (size_t)n * h->nic * 8, cudaMemcpyHostToDevice));
+  // controls: frequencies and knots packed in one aux buffer
+  size_t aux = 0;
+  for (int k = 0; k < h->Nc; ++k) aux += h->ctrl_freqs[k].size() + h->ctrl_knots[k].size();
+  h->d_aux.reserve(std::max<size_t>(aux, 1) * 8);
+  size_t apos = 0;
+  for (int k = 0; k < h->Nc; ++k) {
+    double* base = h->d_aux.as<double>();
+    if (!h->ctrl_freqs[k].empty()) {
+      CUDA_CHECK(cudaMemcpy(base + apos, h->ctrl_freqs[k].data(), h->ctrl_freqs[k].size() * 8, cudaMemcpyHostToDevice));
+      h->ctrls[k].freqs = base + apos; apos += h->ctrl_freqs[k].size();
+    }
+    if (!h->ctrl_knots[k].empty()) {
+      CUDA_CHECK(cudaMemcpy(base + apos, h->ctrl_knots[k].data(), h->ctrl_knots[k].size() * 8, cudaMemcpyHostToDevice));
+      h->ctrls[k].knots = base + apos; apos += h->ctrl_knots[k].size();
+    }
+  }
+  h->d_ctrls.reserve(std::max<size_t>(h->Nc, 1) * sizeof(QgdDevControl));
+  if (h->Nc) CUDA_CHECK(cudaMemcpy(h->d_ctrls.p, h->ctrls.data(), h->Nc * sizeof(QgdDevControl), cudaMemcpyHostToDevice));
+}
+
+// Preconditioner factors for (nsteps, order): form_LHS_no_control (src/forward_evolution.jl:772-802;
+// NOTE as written: I + sum_j (-dt)^j c_j A^j, without the 1/j!) and the two preconditioner types.
+void build_preconditioner(qgd_handle* h, int order) {
+  if (h->pre_key_nsteps == (int)h->nsteps && h->pre_key_order == order) return;
+  const int n = h->N, n2 = h->N2, m = order / 2;
+  const double dt = h->tf / (double)h->nsteps;
+  if (h->precond != QGD_PRECOND_IDENTITY) {
+    for (int dir = 0; dir < 2; ++dir) {
+      dvec A((size_t)n2 * n2, 0.0);
+      for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+          A[i + (size_t)n2 * j] = h->Ss[i + (size_t)n * j];
+          A[i + (size_t)n2 * (j + n)] = h->Ks[i + (size_t)n * j];
+          A[(i + n) + (size_t)n2 * j] = -h->Ks[i + (size_t)n * j];
+          A[(i + n) + (size_t)n2 * (j + n)] = h->Ss[i + (size_t)n * j];
+        }
+      if (dir == 1) {
+        dvec At((size_t)n2 * n2);
+        for (int j = 0; j < n2; ++j) for (int i = 0; i < n2; ++i) At[i + (size_t)n2 * j] = A[j + (size_t)n2 * i];
+        A.swap(At);
+      }
+      dvec Lm((size_t)n2 * n2, 0.0);
+      for (int i = 0; i < n2; ++i) Lm[i + (size_t)n2 * i] = 1.0;
+      for (int j = 1; j <= m; ++j) {
+        const double coeff = ipow(-dt, j) * coefficient(j, m, m);
+        dvec Aj = matpow(A, j, n2);
+        for (size_t e = 0; e < Lm.size(); ++e) Lm[e] += coeff * Aj[e];
+      }
+      if (h->precond == QGD_PRECOND_DIAGONAL) {  // preconditioners.jl:84-126
+        double* pd = reinterpret_cast<double*>(h->blob.data() + h->lay.off_pre[dir]);
+        double* dg = pd; double* up = pd + n2; double* ratio = up + n; double* den = ratio + n;
+        for (int i = 0; i < n2; ++i) {
+          dg[i] = Lm[i + (size_t)n2 * i];
+          if (dg[i] == 0.0) throw QgdError(QGD_EINVAL, "DiagonalHamiltonianPreconditioner: zero diagonal entry in the LHS");
+        }
+        for (int i = 0; i < n; ++i) {
+          up[i] = Lm[i + (size_t)n2 * (i + n)];
+          const double lo = Lm[(i + n) + (size_t)n2 * i];
+          ratio[i] = lo / dg[i];
+          den[i] = dg[n + i] - up[i] * ratio[i];
+        }
+      } else {  // LU: explicit inverse by Gauss-Jordan with partial pivoting
+        dvec M = Lm, Inv((size_t)n2 * n2, 0.0);
+        for (int i = 0; i < n2; ++i) Inv[i + (size_t)n2 * i] = 1.0;
+        for (int k = 0; k < n2; ++k) {
+          int pv = k; double mx = std::fabs(M[k + (size_t)n2 * k]);
+          for (int i = k + 1; i < n2; ++i) if (std::fabs(M[i + (size_t)n2 * k]) > mx) { mx = std::fabs(M[i + (size_t)n2 * k]); pv = i; }
+          if (mx == 0.0) throw QgdError(QGD_EINVAL, "LUPreconditioner: singular LHS");
+          if (pv != k) for (int j = 0; j < n2; ++j) { std::swap(M[k + (size_t)n2 * j], M[pv + (size_t)n2 * j]); std::swap(Inv[k + (size_t)n2 * j], Inv[pv + (size_t)n2 * j]); }
+          const double dinv = 1.0 / M[k + (size_t)n2 * k];
+          for (int j = 0; j < n2; ++j) { M[k + (size_t)n2 * j] *= dinv; Inv[k + (size_t)n2 * j] *= dinv; }
+          for (int i = 0; i < n2; ++i) {
+            if (i == k) continue;
+            const double f = M[i + (size_t)n2 * k];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n2; ++j) { M[i + (size_t)n2 * j] -= f * M[k + (size_t)n2 * j]; Inv[i + (size_t)n2 * j] -= f * Inv[k + (size_t)n2 * j]; }
+          }
+        }
+        h->d_minv[dir].reserve(Inv.size() * 8);
+        CUDA_CHECK(cudaMemcpy(h->d_minv[dir].p, Inv.data(), Inv.size() * 8, cudaMemcpyHostToDevice));
+      }
+    }
+  }
+  h->d_blob.reserve(h->blob.size());
+  CUDA_CHECK(cudaMemcpy(h->d_blob.p, h->blob.data(), h->blob.size(), cudaMemcpyHostToDevice));
+  h->pre_key_nsteps = (int)h->nsteps; h->pre_key_order = order;
+  h->hist_valid = false;
+}
+
+QgdDevProb make_devprob(qgd_handle* h, int order) {
+  QgdDevProb d{};
+  const int m = order / 2;
+  d.N = h->N; d.N2 = h->N2; d.Nc = h->Nc; d.nic = h->nic; d.Ness = h->Ness;
+  d.col0 = h->col0; d.ncol = h->ncol; d.m = m; d.nsteps = (int)h->nsteps; d.P = h->P; d.precond = h->precond;
+  d.dt = h->tf / (double)h->nsteps; d.tf = h->tf; d.abstol = h->abstol; d.reltol = h->reltol;
+  for (int j = 0; j <= m; ++j) {
+    const double cj = coefficient(j, m, m);
+    d.a_rhs[j] = ipow(d.dt, j) * cj;
+    d.a_lhs[j] = ipow(-d.dt, j) * cj;
+    d.a_tay[j] = ipow(d.dt, j) / factorial_d(j);
+  }
+  d.lay = h->lay;
+  d.blob = h->d_blob.as<unsigned char>();
+  d.minv[0] = h->d_minv[0].as<double>(); d.minv[1] = h->d_minv[1].as<double>();
+  d.u0 = h->d_u0.as<double>(); d.v0 = h->d_v0.as<double>();
+  d.table = h->d_table.as<double>();
+  return d;
+}
+
+void check_order(int order) {
+  if (order < 2 || (order & 1) || order / 2 > QGD_MAX_M)
+    throw QgdError(QGD_EINVAL, "order must be even and between 2 and " + std::to_string(2 * QGD_MAX_M));
+}
+
+// control basis table for t_n = n dt, n = 0..nsteps (cached per (nsteps, m))
+void ensure_table(qgd_handle* h, int m) {
+  if (h->tab_key_nsteps == (int)h->nsteps && h->tab_key_m == m) return;
+  const int Nt = (int)h->nsteps + 1;
+  const size_t sz = (size_t)Nt * 2 * (m + 1) * std::max(h->P, 1);
+  h->d_table.reserve(sz * 8);
+  if (h->Nc > 0) {
+    const int threads = 128, total = Nt * h->Nc;
+    k_control_table<<<(total + threads - 1) / threads, threads, 0, h->stream>>>(
+        h->d_ctrls.as<QgdDevControl>(), h->Nc, h->P, m, Nt, nullptr, 0.0, h->tf / (double)h->nsteps, h->d_table.as<double>());
+    CUDA_CHECK(cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  h->tab_key_nsteps = (int)h->nsteps; h->tab_key_m = m;
+}
+
+void compute_cvals(qgd_handle* h, int m, int B, const double* d_pcof) {
+  const int Nt = (int)h->nsteps + 1;
+  const size_t total = (size_t)B * Nt * 2 * (m + 1) * h->Nc;
+  h->d_cvals.reserve(std::max<size_t>(total, 1) * 8);
+  if (total == 0) return;
+  const int threads = 256;
+  k_control_values<<<(unsigned)((total + threads - 1) / threads), threads, 0, h->stream>>>(
+      h->d_ctrls.as<QgdDevControl>(), h->Nc, h->P, m, Nt, h->d_table.as<double>(), d_pcof, B, h->d_cvals.as<double>());
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+}
+
+#define QGD_DISPATCH_EL(el, NAME, ...)            \
+  switch (el) {                                   \
+    case 1: NAME##_1(__VA_ARGS__); break;         \
+    case 2: NAME##_2(__VA_ARGS__); break;         \
+    default: NAME##_4(__VA_ARGS__); break;        \
+  }
+
+void h2d(qgd_handle* h, void* dst, const void* src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes += (int64_t)bytes;
+}
+void d2h(qgd_handle* h, void* dst, const void* src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += (int64_t)bytes;
+}
+void iters_out(qgd_handle* h, int64_t* dst, DevBuf& src, size_t n) {  // device int32 -> host int64
+  if (!dst) return;
+  std::vector<int> tmp(n);
+  d2h(h, tmp.data(), src.p, n * 4);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < n; ++i) dst[i] = tmp[i];
+}
+
+void reset_stats(qgd_handle* h) { h->stats = qgd_stats_t{}; }
+
+// forward sweep on device for B control vectors already in d_pcof
+void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t save_every, bool want_iters) {
+  check_order(order);
+  if (save_every < 1) throw QgdError(QGD_EINVAL, "saveEveryNsteps must be >= 1");
+  const int m = order / 2, el = pick_el(h->N);
+  build_preconditioner(h, order);
+  ensure_table(h, m);
+  compute_cvals(h, m, B, d_pcof);
+  QgdDevProb d = make_devprob(h, order);
+  SweepArgs a{};
+  a.B = B; a.save_every = (int)save_every; a.nslots = 1 + (int)(h->nsteps / save_every);
+  a.cvals = h->d_cvals.as<double>();
+  const size_t hist_sz = (size_t)h->N2 * (m + 1) * a.nslots * h->ncol * B;
+  h->d_history.reserve(hist_sz * 8);
+  h->d_final.reserve((size_t)h->N2 * h->ncol * B * 8);
+  if (h->nsteps % save_every != 0 || save_every != 1)  // slots that are never written must read as zero
+    CUDA_CHECK(cudaMemsetAsync(h->d_history.p, 0, hist_sz * 8, h->stream));
+  a.history = h->d_history.as<double>();
+  a.final_state = h->d_final.as<double>();
+  if (want_iters) { h->d_iters_f.reserve((size_t)h->nsteps * h->ncol * B * 4); a.iters = h->d_iters_f.as<int>(); }
+  CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
+  QGD_DISPATCH_EL(el, launch_forward, h, d, a);
+  CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+  h->hist_B = B; h->hist_order = order; h->hist_nsteps = h->nsteps; h->hist_save = save_every; h->hist_valid = true;
+}
+
+// guard partials + (optionally) forcing array from the device-resident history
+void run_guard(qgd_handle* h, int B, int order, bool want_forcing) {
+  const int m = order / 2, el = pick_el(h->N);
+  QgdDevProb d = make_devprob(h, order);
+  SweepArgs a{};
+  a.B = B; a.save_every = 1; a.nslots = (int)h->nsteps + 1;
+  a.history = h->d_history.as<double>();
+  h->d_guardcol.reserve((size_t)h->ncol * B * 8);
+  a.guardcol = h->d_guardcol.as<double>();
+  if (want_forcing) { h->d_forcing.reserve((size_t)h->N2 * (h->nsteps + 1) * h->ncol * B * 8); a.forcing_out = h->d_forcing.as<double>(); }
+  (void)m;
+  QGD_DISPATCH_EL(el, launch_guard, h, d, a);
+}
+
+// infidelity + terminal condition from d_final_all, then backward sweep and the column reduction
+void run_adjoint(qgd_handle* h, int B, int order, const double* d_target, bool want_iters, bool want_lambda0,
+                 double* d_grad_out, double* d_infid_out, double* d_guard_out) {
+  const int m = order / 2, el = pick_el(h->N);
+  QgdDevProb d = make_devprob(h, order);
+  SweepArgs a{};
+  a.B = B; a.save_every = 1; a.nslots = (int)h->nsteps + 1;
+  a.cvals = h->d_cvals.as<double>();
+  a.history = h->d_history.as<double>();
+  a.final_all = h->d_final_all.as<double>();
+  a.target = d_target;
+  h->d_terminal.reserve((size_t)h->N2 * h->nic * B * 8);
+  a.terminal_out = h->d_terminal.as<double>();
+  a.terminal = h->d_terminal.as<double>();
+  a.infidelity = d_infid_out;
+  if (want_iters) {
+    h->d_iters_t.reserve((size_t)h->nic * B * 4);
+    h->d_iters_a.reserve((size_t)h->nsteps * h->ncol * B * 4);
+    CUDA_CHECK(cudaMemsetAsync(h->d_iters_a.p, 0, (size_t)h->nsteps * h->ncol * B * 4, h->stream));
+    a.iters_term = h->d_iters_t.as<int>();
+  }
+  QGD_DISPATCH_EL(el, launch_terminal, h, d, a);
+  a.iters = want_iters ? h->d_iters_a.as<int>() : nullptr;
+  if (want_lambda0) {
+    const size_t sz = (size_t)h->N2 * (h->nsteps + 1) * h->ncol * B * 8;
+    h->d_lambda0.reserve(sz);
+    CUDA_CHECK(cudaMemsetAsync(h->d_lambda0.p, 0, sz, h->stream));
+    a.lambda0 = h->d_lambda0.as<double>();
+  }
+  h->d_gradcol.reserve((size_t)std::max(h->P, 1) * h->ncol * B * 8);
+  a.gradcol = h->d_gradcol.as<double>();
+  CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
+  QGD_DISPATCH_EL(el, launch_backward, h, d, a);
+  CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
+  const size_t tot = std::max<size_t>((size_t)h->P * B, (size_t)B);
+  k_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->P, h->ncol, B, h->d_gradcol.as<double>(),
+                                                                  h->d_guardcol.as<double>(), d_grad_out, d_guard_out);
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+  (void)m;
+}
+
+void finish_timing(qgd_handle* h, bool fwd, bool bwd) {
+  float ms = 0;
+  if (fwd) { cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->stats.last_forward_ms = ms; }
+  if (bwd) { cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->stats.last_backward_ms = ms; }
+  if (fwd && bwd) { cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]); h->stats.last_total_ms = ms; }
+}
+
+int guarded(const std::function<void()>& f) {
+  try { f(); return QGD_OK; }
+  catch (const QgdError& e) { g_err = e.what(); return e.code; }
+  catch (const std::exception& e) { g_err = e.what(); return QGD_EINVAL; }
+}
+void require(bool ok, const char* msg) { if (!ok) throw QgdError(QGD_EINVAL, msg); }
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+const char* qgd_last_error(void) { return g_err.c_str(); }
+
+int64_t qgd_control_n_coeff(const qgd_control_t* c) {
+  int64_t base = 0;
+  if (c->type == QGD_CONTROL_GRAPE) base = 2 * c->n_amplitudes;
+  else if (c->type == QGD_CONTROL_BSPLINE2) base = 2 * c->D1;
+  else if (c->type == QGD_CONTROL_FORTRAN_BSPLINE) base = 2 * c->n_basis;
+  return c->n_carriers > 0 ? base * c->n_carriers : base;
+}
+int64_t qgd_problem_n_coeff(const qgd_problem_t* p) {
+  int64_t s = 0;
+  for (int64_t k = 0; k < p->N_operators; ++k) s += qgd_control_n_coeff(&p->controls[k]);
+  return s;
+}
+
+int qgd_create(const qgd_problem_t* prob, int device, qgd_handle_t** out) {
+  qgd_handle* h = nullptr;
+  int rc = guarded([&]() {
+    require(out != nullptr, "null output handle");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw QgdError(QGD_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
+    CUDA_CHECK(cudaSetDevice(device));
+    h = new qgd_handle();
+    h->device = device;
+    CUDA_CHECK(cudaGetDeviceProperties(&h->prop, device));
+    if (h->prop.major < 10) throw QgdError(QGD_ECUDA, "device is not sm_100 class (Blackwell B200 required)");
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) CUDA_CHECK(cudaEventCreate(&ev));
+    validate_and_load(h, prob);
+    *out = h;
+  });
+  if (rc != QGD_OK && h) { qgd_destroy(h); }
+  return rc;
+}
+
+int qgd_destroy(qgd_handle_t* h) {
+  if (!h) return QGD_OK;
+  cudaSetDevice(h->device);
+  DevBuf* bufs[] = {&h->d_blob, &h->d_minv[0], &h->d_minv[1], &h->d_u0, &h->d_v0, &h->d_ctrls, &h->d_aux, &h->d_table, &h->d_pcof,
+                    &h->d_cvals, &h->d_history, &h->d_final, &h->d_final_all, &h->d_terminal, &h->d_lambda0, &h->d_lamhist,
+                    &h->d_gradcol, &h->d_grad, &h->d_guardcol, &h->d_guard, &h->d_infid, &h->d_iters_f, &h->d_iters_a,
+                    &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return QGD_OK;
+}
+
+int qgd_set_nsteps(qgd_handle_t* h, int64_t nsteps) {
+  return guarded([&]() { require(h && nsteps >= 1, "nsteps must be >= 1"); h->nsteps = nsteps; h->hist_valid = false; });
+}
+int qgd_set_gmres_tolerances(qgd_handle_t* h, double abstol, double reltol) {
+  return guarded([&]() { require(h != nullptr, "null handle"); h->abstol = abstol; h->reltol = reltol; h->hist_valid = false; });
+}
+int qgd_set_column_shard(qgd_handle_t* h, int64_t col_begin, int64_t col_count) {
+  return guarded([&]() {
+    require(h && col_begin >= 0 && col_count >= 1 && col_begin + col_count <= h->nic, "column shard out of range");
+    h->col0 = (int)col_begin; h->ncol = (int)col_count; h->hist_valid = false;
+  });
+}
+
+int qgd_eval_forward(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32_t order, int64_t save_every, double* history,
+                     double* final_state, int64_t* gmres_iters) {
+  return guarded([&]() {
+    require(h && pcof && n_batch >= 1, "bad arguments");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    const int B = (int)n_batch, m = order / 2;
+    h->d_pcof.reserve((size_t)std::max(h->P, 1) * B * 8);
+    h2d(h, h->d_pcof.p, pcof, (size_t)h->P * B * 8);
+    run_forward(h, h->d_pcof.as<double>(), B, order, save_every, gmres_iters != nullptr);
+    const int nslots = 1 + (int)(h->nsteps / save_every);
+    if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * nslots * h->ncol * B * 8);
+    if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
+    finish_timing(h, true, false);
+  });
+}
+
+int qgd_adjoint_phase1(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32_t order, double* final_state_local,
+                       double* guard_local) {
+  return guarded([&]() {
+    require(h && pcof && n_batch >= 1, "bad arguments");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    const int B = (int)n_batch;
+    h->d_pcof.reserve((size_t)std::max(h->P, 1) * B * 8);
+    h2d(h, h->d_pcof.p, pcof, (size_t)h->P * B * 8);
+    run_forward(h, h->d_pcof.as<double>(), B, order, 1, false);
+    run_guard(h, B, order, false);
+    h->d_guard.reserve((size_t)B * 8);
+    h->d_grad.reserve((size_t)std::max(h->P, 1) * B * 8);
+    h->d_gradcol.reserve((size_t)std::max(h->P, 1) * h->ncol * B * 8);
+    CUDA_CHECK(cudaMemsetAsync(h->d_gradcol.p, 0, (size_t)std::max(h->P, 1) * h->ncol * B * 8, h->stream));
+    k_finalize<<<(unsigned)(((size_t)std::max(h->P, 1) * B + 255) / 256), 256, 0, h->stream>>>(
+        h->P, h->ncol, B, h->d_gradcol.as<double>(), h->d_guardcol.as<double>(), h->d_grad.as<double>(), h->d_guard.as<double>());
+    CUDA_CHECK(cudaGetLastError());
+    h->stats.kernel_launches++;
+    if (final_state_local) d2h(h, final_state_local, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
+    if (guard_local) d2h(h, guard_local, h->d_guard.p, (size_t)B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->phase_B = B; h->phase_order = order;
+    finish_timing(h, true, false);
+  });
+}
+
+int qgd_adjoint_phase2(qgd_handle_t* h, const double* target, const double* final_state_all, double* grad_local, double* infidelity) {
+  return guarded([&]() {
+    require(h && target && final_state_all, "bad arguments");
+    if (!h->hist_valid || h->phase_B < 1) throw QgdError(QGD_ESTATE, "qgd_adjoint_phase2 without a preceding qgd_adjoint_phase1");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const int B = h->phase_B, order = h->phase_order;
+    h->d_target.reserve((size_t)h->N2 * h->nic * 8);
+    h2d(h, h->d_target.p, target, (size_t)h->N2 * h->nic * 8);
+    h->d_final_all.reserve((size_t)h->N2 * h->nic * B * 8);
+    h2d(h, h->d_final_all.p, final_state_all, (size_t)h->N2 * h->nic * B * 8);
+    h->d_infid.reserve((size_t)B * 8);
+    h->d_grad.reserve((size_t)std::max(h->P, 1) * B * 8);
+    run_adjoint(h, B, order, h->d_target.as<double>(), false, false, h->d_grad.as<double>(), h->d_infid.as<double>(), nullptr);
+    if (grad_local) d2h(h, grad_local, h->d_grad.p, (size_t)h->P * B * 8);
+    if (infidelity) d2h(h, infidelity, h->d_infid.p, (size_t)B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    finish_timing(h, false, true);
+  });
+}
+
+int qgd_discrete_adjoint(qgd_handle_t* h, const double* pcof, int64_t n_batch, const double* target, int32_t order,
+                         int32_t history_precomputed, double* grad, double* infidelity, double* guard_penalty, double* history,
+                         double* lambda_history, double* adjoint_forcing, int64_t* iters_fwd, int64_t* iters_adj, int64_t* iters_term) {
+  return guarded([&]() {
+    require(h && pcof && target && n_batch >= 1, "bad arguments");
+    if (h->ncol != h->nic) throw QgdError(QGD_ESTATE, "column-sharded handle: use qgd_adjoint_phase1/phase2");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    check_order(order);
+    const int B = (int)n_batch, m = order / 2;
+    const size_t Nt = (size_t)h->nsteps + 1;
+    h->d_pcof.reserve((size_t)std::max(h->P, 1) * B * 8);
+    h2d(h, h->d_pcof.p, pcof, (size_t)h->P * B * 8);
+    h->d_target.reserve((size_t)h->N2 * h->nic * 8);
+    h2d(h, h->d_target.p, target, (size_t)h->N2 * h->nic * 8);
+    const bool want_iters = iters_fwd || iters_adj || iters_term;
+    if (history_precomputed) {
+      if (!(h->hist_valid && h->hist_B == B && h->hist_order == order && h->hist_nsteps == h->nsteps && h->hist_save == 1))
+        throw QgdError(QGD_ESTATE, "history_precomputed: no matching history is resident on the device (call qgd_eval_forward with "
+                                   "saveEveryNsteps=1, the same batch and order first)");
+      build_preconditioner(h, order);
+      ensure_table(h, m);
+      compute_cvals(h, m, B, h->d_pcof.as<double>());
+      CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
+      CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+    } else {
+      run_forward(h, h->d_pcof.as<double>(), B, order, 1, want_iters);
+    }
+    run_guard(h, B, order, adjoint_forcing != nullptr);
+    // all columns are local: the final states are the terminal kernel's input as they are
+    h->d_final_all.reserve((size_t)h->N2 * h->nic * B * 8);
+    CUDA_CHECK(cudaMemcpyAsync(h->d_final_all.p, h->d_final.p, (size_t)h->N2 * h->nic * B * 8, cudaMemcpyDeviceToDevice, h->stream));
+    h->d_infid.reserve((size_t)B * 8); h->d_guard.reserve((size_t)B * 8);
+    h->d_grad.reserve((size_t)std::max(h->P, 1) * B * 8);
+    run_adjoint(h, B, order, h->d_target.as<double>(), want_iters, lambda_history != nullptr, h->d_grad.as<double>(),
+                h->d_infid.as<double>(), h->d_guard.as<double>());
+    if (lambda_history) {
+      const int el = pick_el(h->N);
+      const size_t sz = (size_t)h->N2 * (m + 1) * Nt * h->ncol * B * 8;
+      h->d_lamhist.reserve(sz);
+      QgdDevProb d = make_devprob(h, order);
+      SweepArgs a{};
+      a.B = B; a.cvals = h->d_cvals.as<double>(); a.lambda0 = h->d_lambda0.as<double>();
+      QGD_DISPATCH_EL(el, launch_lambda_columns, h, d, a, h->d_lamhist.as<double>());
+      d2h(h, lambda_history, h->d_lamhist.p, sz);
+    }
+    if (grad) d2h(h, grad, h->d_grad.p, (size_t)h->P * B * 8);
+    if (infidelity) d2h(h, infidelity, h->d_infid.p, (size_t)B * 8);
+    if (guard_penalty) d2h(h, guard_penalty, h->d_guard.p, (size_t)B * 8);
+    if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * Nt * h->ncol * B * 8);
+    if (adjoint_forcing) d2h(h, adjoint_forcing, h->d_forcing.p, (size_t)h->N2 * Nt * h->ncol * B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    if (!history_precomputed) iters_out(h, iters_fwd, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
+    iters_out(h, iters_adj, h->d_iters_a, (size_t)h->nsteps * h->ncol * B);
+    iters_out(h, iters_term, h->d_iters_t, (size_t)h->nic * B);
+    finish_timing(h, true, true);
+  });
+}
+
+int qgd_discrete_adjoint_device(qgd_handle_t* h, const double* d_pcof, int64_t n_batch, const double* d_target, int32_t order,
+                                double* d_grad, double* d_infidelity, double* d_guard_penalty, void* stream) {
+  return guarded([&]() {
+    require(h && d_pcof && d_target && d_grad && d_infidelity && d_guard_penalty && n_batch >= 1, "bad arguments");
+    if (h->ncol != h->nic) throw QgdError(QGD_ESTATE, "column-sharded handle: use qgd_adjoint_phase1/phase2");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    cudaStream_t own = h->stream;
+    if (stream) h->stream = reinterpret_cast<cudaStream_t>(stream);
+    try {
+      const int B = (int)n_batch;
+      run_forward(h, d_pcof, B, order, 1, false);
+      run_guard(h, B, order, false);
+      h->d_final_all.reserve((size_t)h->N2 * h->nic * B * 8);
+      CUDA_CHECK(cudaMemcpyAsync(h->d_final_all.p, h->d_final.p, (size_t)h->N2 * h->nic * B * 8, cudaMemcpyDeviceToDevice, h->stream));
+      run_adjoint(h, B, order, d_target, false, false, d_grad, d_infidelity, d_guard_penalty);
+    } catch (...) { h->stream = own; throw; }
+    h->stream = own;
+  });
+}
+
+int qgd_infidelity_real(qgd_handle_t* h, const double* final_state, const double* target, int64_t n_batch, double* infidelity) {
+  return guarded([&]() {
+    require(h && final_state && target && infidelity && n_batch >= 1, "bad arguments");
+    // tiny host-independent reduction done on the device for consistency with the gradient path
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const int B = (int)n_batch;
+    std::vector<double> out(B);
+    const int N = h->N, N2 = h->N2;
+    for (int b = 0; b < B; ++b) {  // O(2N*nic) work; objective-only calls are host side in the reference too
+      double dR = 0, dT = 0;
+      for (int c = 0; c < h->nic; ++c)
+        for (int r = 0; r < N; ++r) {
+          const double pu = final_state[r + (size_t)N2 * (c + (size_t)h->nic * b)], pv = final_state[N + r + (size_t)N2 * (c + (size_t)h->nic * b)];
+          const double Ru = target[r + (size_t)N2 * c], Rv = target[N + r + (size_t)N2 * c];
+          dR += pu * Ru + pv * Rv;
+          dT += pu * Rv - pv * Ru;
+        }
+      infidelity[b] = 1.0 - (dR * dR + dT * dT) / ((double)h->Ness * (double)h->Ness);
+    }
+  });
+}
+
+int qgd_eval_controls(qgd_handle_t* h, const double* pcof, const double* times, int64_t ntimes, int32_t nderiv, double* p_out,
+                      double* q_out, double* gp_out, double* gq_out) {
+  return guarded([&]() {
+    require(h && times && ntimes >= 1 && nderiv >= 1 && nderiv <= QGD_MAX_M + 1, "bad arguments");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const int m = nderiv - 1, nt = (int)ntimes, P = std::max(h->P, 1);
+    DevBuf d_times, d_tab, d_pc, d_cv;
+    try {
+      d_times.reserve((size_t)nt * 8);
+      CUDA_CHECK(cudaMemcpyAsync(d_times.p, times, (size_t)nt * 8, cudaMemcpyHostToDevice, h->stream));
+      const size_t tsz = (size_t)nt * 2 * nderiv * P;
+      d_tab.reserve(tsz * 8);
+      k_control_table<<<(nt * h->Nc + 127) / 128, 128, 0, h->stream>>>(h->d_ctrls.as<QgdDevControl>(), h->Nc, h->P, m, nt,
+                                                                      d_times.as<double>(), 0.0, 0.0, d_tab.as<double>());
+      CUDA_CHECK(cudaGetLastError());
+      std::vector<double> tab(tsz);
+      if (gp_out || gq_out) {
+        CUDA_CHECK(cudaMemcpyAsync(tab.data(), d_tab.p, tsz * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        // table is Taylor scaled; the reference's eval_grad_* are un-scaled: multiply r! back
+        for (int n = 0; n < nt; ++n)
+          for (int r = 0; r < nderiv; ++r) {
+            const double f = factorial_d(r);
+            for (int t = 0; t < h->P; ++t) {
+              if (gp_out) gp_out[t + (size_t)h->P * (r + (size_t)nderiv * n)] = tab[(((size_t)n * 2 + 0) * nderiv + r) * P + t] * f;
+              if (gq_out) gq_out[t + (size_t)h->P * (r + (size_t)nderiv * n)] = tab[(((size_t)n * 2 + 1) * nderiv + r) * P + t] * f;
+            }
+          }
+      }
+      if (p_out || q_out) {
+        require(pcof != nullptr, "pcof required for control values");
+        d_pc.reserve((size_t)P * 8);
+        CUDA_CHECK(cudaMemcpyAsync(d_pc.p, pcof, (size_t)h->P * 8, cudaMemcpyHostToDevice, h->stream));
+        const size_t total = (size_t)nt * 2 * nderiv * h->Nc;
+        d_cv.reserve(std::max<size_t>(total, 1) * 8);
+        k_control_values<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->d_ctrls.as<QgdDevControl>(), h->Nc, h->P, m, nt,
+                                                                                d_tab.as<double>(), d_pc.as<double>(), 1, d_cv.as<double>());
+        CUDA_CHECK(cudaGetLastError());
+        std::vector<double> cv(total);
+        CUDA_CHECK(cudaMemcpyAsync(cv.data(), d_cv.p, total * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        for (int n = 0; n < nt; ++n)
+          for (int r = 0; r < nderiv; ++r)
+            for (int k = 0; k < h->Nc; ++k) {
+              if (p_out) p_out[r + (size_t)nderiv * (k + (size_t)h->Nc * n)] = cv[(((size_t)n * 2 + 0) * nderiv + r) * h->Nc + k];
+              if (q_out) q_out[r + (size_t)nderiv * (k + (size_t)h->Nc * n)] = cv[(((size_t)n * 2 + 1) * nderiv + r) * h->Nc + k];
+            }
+      }
+    } catch (...) { d_times.release(); d_tab.release(); d_pc.release(); d_cv.release(); throw; }
+    d_times.release(); d_tab.release(); d_pc.release(); d_cv.release();
+  });
+}
+
+int qgd_compute_derivatives(qgd_handle_t* h, double* uv, int64_t ncols_in, int32_t order, const double* cvals_re,
+                            const double* cvals_im, int32_t adjoint) {
+  return guarded([&]() {
+    require(h && uv && cvals_re && cvals_im && ncols_in >= 1, "bad arguments");
+    check_order(order);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const int m = order / 2, el = pick_el(h->N);
+    build_preconditioner(h, order);
+    const size_t sz = (size_t)h->N2 * (m + 1) * ncols_in * 8;
+    h->d_scratch.reserve(sz + (size_t)2 * (m + 1) * std::max(h->Nc, 1) * 8);
+    double* d_uv = h->d_scratch.as<double>();
+    double* d_cv = d_uv + (size_t)h->N2 * (m + 1) * ncols_in;
+    CUDA_CHECK(cudaMemcpyAsync(d_uv, uv, sz, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_cv, cvals_re, (size_t)(m + 1) * h->Nc * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_CHECK(cudaMemcpyAsync(d_cv + (size_t)(m + 1) * h->Nc, cvals_im, (size_t)(m + 1) * h->Nc * 8, cudaMemcpyHostToDevice, h->stream));
+    QgdDevProb d = make_devprob(h, order);
+    // the host passes [1+m, Nc] column-major = device layout [k][r]; device wants [r][k]: transpose on the fly
+    std::vector<double> cv((size_t)2 * (m + 1) * std::max(h->Nc, 1));
+    for (int r = 0; r <= m; ++r)
+      for (int k = 0; k < h->Nc; ++k) {
+        cv[((size_t)0 * (m + 1) + r) * h->Nc + k] = cvals_re[r + (size_t)(m + 1) * k];
+        cv[((size_t)1 * (m + 1) + r) * h->Nc + k] = cvals_im[r + (size_t)(m + 1) * k];
+      }
+    CUDA_CHECK(cudaMemcpyAsync(d_cv, cv.data(), cv.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    SweepArgs a{};
+    QGD_DISPATCH_EL(el, launch_derivs, h, d, a, d_uv, (int)ncols_in, d_cv, adjoint);
+    CUDA_CHECK(cudaMemcpyAsync(uv, d_uv, sz, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int qgd_get_stats(qgd_handle_t* h, qgd_stats_t* out) {
+  return guarded([&]() { require(h && out, "bad arguments"); *out = h->stats; });
+}
+
+int qgd_measure_fp64_peak(int device, double* tflops) {
+  return guarded([&]() {
+    require(tflops != nullptr, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw QgdError(QGD_ECUDA, "no CUDA device available");
+    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 1 << 15;
+    double* d_out = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_out, (size_t)threads * blocks * 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+      cudaEventRecord(e0);
+      qgd::k_fp64_peak<<<blocks, threads>>>(d_out, iters);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+      if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+  });
+}
+
+}  // extern "C"

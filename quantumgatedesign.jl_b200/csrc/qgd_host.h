@@ -1,0 +1,90 @@
+// qgd_host.h -- host-side types shared by the API translation unit and the per-EL kernel instantiation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/qgd_b200.h"
+#include "qgd_common.h"
+
+namespace qgd {
+struct SweepArgs;
+}
+
+struct QgdError : std::runtime_error {
+  int code;
+  QgdError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t e_ = (expr);                                                                               \
+    if (e_ != cudaSuccess)                                                                                 \
+      throw QgdError(e_ == cudaErrorMemoryAllocation ? QGD_ENOMEM : QGD_ECUDA,                              \
+                     std::string(#expr) + ": " + cudaGetErrorString(e_));                                  \
+  } while (0)
+
+typedef std::vector<double> dvec;
+
+struct DevBuf {  // grow-only device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    CUDA_CHECK(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct qgd_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop;
+  // problem
+  int N = 0, N2 = 0, Nc = 0, nic = 0, Ness = 0, P = 0, precond = 0;
+  int64_t nsteps = 0;
+  double tf = 0, abstol = 0, reltol = 0;
+  int col0 = 0, ncol = 0;
+  dvec Ks, Ss;  // dense drift (preconditioner setup)
+  std::vector<QgdDevControl> ctrls;
+  std::vector<dvec> ctrl_freqs, ctrl_knots;
+  // operator blob
+  QgdOpLayout lay;
+  std::vector<unsigned char> blob;
+  int pre_key_nsteps = -1, pre_key_order = -1;
+  DevBuf d_blob, d_minv[2], d_u0, d_v0, d_ctrls, d_aux;
+  // control table cache
+  int tab_key_nsteps = -1, tab_key_m = -1;
+  DevBuf d_table;
+  // batch buffers
+  DevBuf d_pcof, d_cvals, d_history, d_final, d_final_all, d_terminal, d_lambda0, d_lamhist, d_gradcol, d_grad, d_guardcol,
+      d_guard, d_infid, d_iters_f, d_iters_a, d_iters_t, d_target, d_forcing, d_V, d_H, d_scratch;
+  // state of the device-resident history
+  int hist_B = 0, hist_order = 0;
+  int64_t hist_nsteps = 0, hist_save = 0;
+  bool hist_valid = false;
+  int phase_B = 0, phase_order = 0;  // two-phase API
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  qgd_stats_t stats{};
+};
+
+// Kernel launchers, one set per EL = levels per lane (instantiated in qgd_inst_el*.cu).
+#define QGD_DECLARE_LAUNCHERS(EL)                                                                                   \
+  void launch_forward_##EL(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a);                                          \
+  void launch_guard_##EL(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a);                                            \
+  void launch_terminal_##EL(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a);                                         \
+  void launch_backward_##EL(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a);                                         \
+  void launch_lambda_columns_##EL(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, double* lam_hist);                 \
+  void launch_derivs_##EL(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, double* uv, int ncols, const double* cv, int adjoint);
+
+QGD_DECLARE_LAUNCHERS(1)
+QGD_DECLARE_LAUNCHERS(2)
+QGD_DECLARE_LAUNCHERS(4)

@@ -1,0 +1,400 @@
+// qgd_kernels.cuh -- the persistent sweep kernels (sm_100a).
+//
+//   k_forward   K2/K3: forward Hermite sweep, one warp per (control vector, column); marches all
+//               time steps on-device (eval_forward!, reference src/forward_evolution.jl:88-245).
+//   k_guard     K4a: guard penalty partials and guard forcing (src/infidelity.jl:56-96,
+//               src/eval_grad_discrete_adjoint.jl:732-752).
+//   k_terminal  K4b: infidelity + terminal condition (src/infidelity.jl:7-18,
+//               src/eval_grad_discrete_adjoint.jl:1-67), one warp per control vector.
+//   k_backward  K5: adjoint sweep + gradient accumulation (eval_adjoint!, src/forward_evolution.jl:
+//               352-483; accumulate_gradient!, src/eval_grad_discrete_adjoint.jl:582-726).
+//   k_finalize  K6 (single GPU part): fixed-order reduction of the per-column partials.
+//
+// The operator blob (Hamiltonian blocks in row-ELL form, guard projector, preconditioner diagonals) is
+// staged into shared memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier).
+#pragma once
+#include "qgd_warp.cuh"
+
+namespace qgd {
+
+struct SweepArgs {
+  int B;                 // control vectors in this batch
+  int save_every, nslots;
+  int warp_smem_doubles; // per-warp shared-memory region
+  const double* cvals;   // [B][nsteps+1][2][m+1][Nc]
+  double* history;       // [2N][1+m][nslots][ncol][B]
+  double* final_state;   // [2N][ncol][B]
+  int* iters;            // [nsteps][ncol][B] or null
+  double* Vws;           // Krylov workspaces, one per resident warp
+  double* Hws;
+  size_t v_stride, h_stride;
+  // backward sweep
+  const double* terminal;  // [2N][nic][B]   lambda_N of every column
+  double* lambda0;         // [2N][nsteps+1][ncol][B] (lambda itself, Taylor column 0) or null
+  double* gradcol;         // [P][ncol][B]
+  // guard
+  double* guardcol;        // [ncol][B]
+  double* forcing_out;     // [2N][nsteps+1][ncol][B] or null
+  // terminal
+  const double* final_all; // [2N][nic][B]
+  const double* target;    // [2N][nic]
+  double* terminal_out;    // [2N][nic][B]
+  double* infidelity;      // [B]
+  int* iters_term;         // [nic][B] or null
+};
+
+// ---- TMA bulk copy of the operator blob into shared memory ------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ inline void stage_blob(unsigned char* dst, const unsigned char* src, int bytes, unsigned long long* mbar) {
+  const unsigned mb = smem_u32(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"((unsigned)bytes), "r"(mb)
+        : "memory");
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mb)
+        : "memory");
+  }
+}
+
+// Carve the dynamic shared memory: [mbarrier][blob][warp regions]; fills the lane-invariant context.
+__device__ inline WarpCtx make_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem) {
+  WarpCtx c;
+  c.d = &d;
+  c.lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* p = smem + 16;
+  if (d.ops_in_smem) {
+    c.ops = p;
+    p += d.lay.bytes;
+  } else {
+    c.ops = d.blob;
+  }
+  double* w = reinterpret_cast<double*>(p) + (size_t)warp * a.warp_smem_doubles;
+  const int nv = d.m > 2 ? d.m : 2;
+  c.wv = w; w += (size_t)nv * d.N2;
+  c.cv = w; w += 2 * (d.m + 1) * d.Nc;
+  c.hcol = w; w += d.N2 + 1;
+  c.nullv = w; w += d.N2 + 1;
+  c.yv = w; w += d.N2 + 1;
+  const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  c.Vg = a.Vws + slot * a.v_stride;
+  c.Hg = a.Hws + slot * a.h_stride;
+  return c;
+}
+
+// extra per-warp scratch after the WarpCtx arrays (backward sweep: gradient accumulators + g buffer)
+__device__ inline double* warp_extra(const QgdDevProb& d, const WarpCtx& c) { return c.yv + d.N2 + 1; }
+
+// ------------------------------------------------------------------------------------------------------
+template <int EL>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_forward(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (d.ops_in_smem) stage_blob(smem + 16, d.blob, d.lay.bytes, reinterpret_cast<unsigned long long*>(smem));
+  WarpCtx c = make_ctx(d, a, smem);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2, m = d.m;
+  const size_t items = (size_t)a.B * d.ncol;
+  const size_t cv_stride = (size_t)2 * (m + 1) * d.Nc;
+  const size_t slot_sz = (size_t)N2 * (m + 1);
+  FwdOp<EL> op;
+  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+    const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
+    const double* cvb = a.cvals + (size_t)b * (d.nsteps + 1) * cv_stride;
+    double* hist = a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b);
+    Vec<EL> x;
+#pragma unroll
+    for (int e = 0; e < EL; ++e) {
+      const int r = lane + 32 * e;
+      x.u[e] = r < N ? d.u0[r + (size_t)N * col] : 0.0;
+      x.v[e] = r < N ? d.v0[r + (size_t)N * col] : 0.0;
+    }
+    load_cv(c, cvb);
+    for (int n = 0; n < d.nsteps; ++n) {
+      Vec<EL> rhs, guess;
+      double* slot = (n % a.save_every == 0) ? hist + slot_sz * (n / a.save_every) : nullptr;
+      fwd_derivs<EL, true>(c, x, d.a_rhs, rhs, &guess, slot);  // explicit part at t_n
+      load_cv(c, cvb + (size_t)(n + 1) * cv_stride);            // implicit part uses t_{n+1}
+      x = guess;
+      const int it = gmres_warp<EL>(c, op, x, rhs, d.abstol, -1.0, N2, N2, 0);
+      if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
+    }
+    {  // Taylor columns at the final time (forward_evolution.jl:232-242)
+      Vec<EL> dummy, guess;
+      double* slot = (d.nsteps % a.save_every == 0) ? hist + slot_sz * (d.nsteps / a.save_every) : nullptr;
+      fwd_derivs<EL, true>(c, x, d.a_rhs, dummy, &guess, slot);
+      vstore(x, a.final_state + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b), N, lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Guard penalty partial of one (control vector, column) and, optionally, the adjoint forcing array.
+template <int EL>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_guard(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (d.ops_in_smem) stage_blob(smem + 16, d.blob, d.lay.bytes, reinterpret_cast<unsigned long long*>(smem));
+  WarpCtx c = make_ctx(d, a, smem);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2, m = d.m, Nt = d.nsteps + 1;
+  const size_t items = (size_t)a.B * d.ncol;
+  const size_t slot_sz = (size_t)N2 * (m + 1);
+  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+    const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol);
+    const double* hist = a.history + slot_sz * Nt * ((size_t)cl + (size_t)d.ncol * b);
+    double pen = 0.0;
+    for (int n = 0; n < Nt; ++n) {
+      Vec<EL> w0, Ww;
+      vload(w0, hist + slot_sz * n, N, lane);
+      __syncwarp();
+      vstore(w0, c.wv, N, lane);
+      __syncwarp();
+      guard_apply(c, c.wv, Ww);
+      const double wt = (n == 0 || n == Nt - 1) ? 0.5 : 1.0;
+      pen += wt * vdot(w0, Ww);
+      if (a.forcing_out) {
+        double* f = a.forcing_out + (size_t)N2 * ((size_t)n + (size_t)Nt * ((size_t)cl + (size_t)d.ncol * b));
+        const double sc = -2.0 * d.dt / d.tf * wt;
+        vscale(Ww, sc);
+        vstore(Ww, f, N, lane);
+      }
+    }
+    if (lane == 0) a.guardcol[(size_t)cl + (size_t)d.ncol * b] = pen * (d.dt / d.tf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Infidelity and terminal condition; one warp per control vector, columns sequential because the
+// reference carries the GMRES solution of column i-1 over as the initial guess of column i
+// (src/eval_grad_discrete_adjoint.jl:60-64).
+template <int EL>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_terminal(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (d.ops_in_smem) stage_blob(smem + 16, d.blob, d.lay.bytes, reinterpret_cast<unsigned long long*>(smem));
+  WarpCtx c = make_ctx(d, a, smem);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2, m = d.m;
+  const size_t cv_stride = (size_t)2 * (m + 1) * d.Nc;
+  AdjOp<EL> op;
+  for (int b = blockIdx.x * wpc + warp; b < a.B; b += gridDim.x * wpc) {
+    const double* psi = a.final_all + (size_t)N2 * d.nic * b;
+    double dR = 0.0, dT = 0.0;
+    for (int col = 0; col < d.nic; ++col) {
+      Vec<EL> p, R;
+      vload(p, psi + (size_t)N2 * col, N, lane);
+      vload(R, a.target + (size_t)N2 * col, N, lane);
+#pragma unroll
+      for (int e = 0; e < EL; ++e) {
+        dR += p.u[e] * R.u[e] + p.v[e] * R.v[e];
+        dT += p.u[e] * R.v[e] - p.v[e] * R.u[e];  // T = [R_v; -R_u]
+      }
+    }
+    dR = warp_sum(dR);
+    dT = warp_sum(dT);
+    const double ness2 = (double)d.Ness * (double)d.Ness;
+    if (lane == 0) a.infidelity[b] = 1.0 - (dR * dR + dT * dT) / ness2;
+    load_cv(c, a.cvals + ((size_t)b * (d.nsteps + 1) + d.nsteps) * cv_stride);  // controls at t = tf
+    Vec<EL> x;
+    vzero(x);
+    const double sc = 2.0 / ness2;
+    const int restart = N2 < 20 ? N2 : 20;
+    for (int col = 0; col < d.nic; ++col) {
+      Vec<EL> p, R, Ww, rhs;
+      vload(p, psi + (size_t)N2 * col, N, lane);
+      vload(R, a.target + (size_t)N2 * col, N, lane);
+      __syncwarp();
+      vstore(p, c.wv, N, lane);
+      __syncwarp();
+      guard_apply(c, c.wv, Ww);
+      __syncwarp();
+      const double fsc = -2.0 * d.dt / d.tf * 0.5;  // forcing[:, end, :]
+#pragma unroll
+      for (int e = 0; e < EL; ++e) {
+        rhs.u[e] = (dR * R.u[e] + dT * R.v[e]) * sc + fsc * Ww.u[e];
+        rhs.v[e] = (dR * R.v[e] + dT * (-R.u[e])) * sc + fsc * Ww.v[e];
+      }
+      const int it = gmres_warp<EL>(c, op, x, rhs, d.abstol, d.reltol, restart, N2, -1);
+      vstore(x, a.terminal_out + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
+      if (a.iters_term && lane == 0) a.iters_term[(size_t)col + (size_t)d.nic * b] = it;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// grad_acc[theta] -= sum_r table_p[r][theta] gK[r][k(theta)] + table_q[r][theta] gS[r][k(theta)]
+__device__ inline void accumulate_grad(const WarpCtx& c, const QgdDevControl* ctrls, const double* table_n,
+                                       const double* gKs, const double* gSs, double* gacc) {
+  const QgdDevProb& d = *c.d;
+  const int nd = d.m + 1, P = d.P;
+  for (int k = 0; k < d.Nc; ++k) {
+    const int off = ctrls[k].offset, nco = ctrls[k].ncoeff;
+    for (int t = c.lane; t < nco; t += 32) {
+      double s = 0.0;
+      for (int r = 0; r < d.m; ++r) {
+        s = fma(table_n[((size_t)0 * nd + r) * P + off + t], gKs[r * (QGD_MAX_OPS - 1) + k], s);
+        s = fma(table_n[((size_t)1 * nd + r) * P + off + t], gSs[r * (QGD_MAX_OPS - 1) + k], s);
+      }
+      gacc[off + t] -= s;
+    }
+  }
+}
+
+template <int EL>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_backward(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
+                                                                       const QgdDevControl* __restrict__ ctrls) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (d.ops_in_smem) stage_blob(smem + 16, d.blob, d.lay.bytes, reinterpret_cast<unsigned long long*>(smem));
+  WarpCtx c = make_ctx(d, a, smem);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2, m = d.m, Nt = d.nsteps + 1, P = d.P;
+  const size_t items = (size_t)a.B * d.ncol;
+  const size_t cv_stride = (size_t)2 * (m + 1) * d.Nc;
+  const size_t slot_sz = (size_t)N2 * (m + 1);
+  const size_t tab_stride = (size_t)2 * (m + 1) * P;
+  double* gacc = warp_extra(d, c);                      // [P]
+  double* gKs = gacc + P;                               // [QGD_MAX_M][QGD_MAX_OPS-1] reduced g^K
+  double* gSs = gKs + QGD_MAX_M * (QGD_MAX_OPS - 1);    // reduced g^S
+  AdjOp<EL> op;
+  double a_imp[QGD_MAX_M + 1];
+  for (int j = 0; j <= m; ++j) a_imp[j] = -d.a_lhs[j];  // -(−dt)^j c_j
+  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+    const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
+    const double* cvb = a.cvals + (size_t)b * Nt * cv_stride;
+    const double* hist = a.history + slot_sz * Nt * ((size_t)cl + (size_t)d.ncol * b);
+    double* lam0 = a.lambda0 ? a.lambda0 + (size_t)N2 * Nt * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
+    for (int t = lane; t < P; t += 32) gacc[t] = 0.0;
+    Vec<EL> lam;
+    vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
+    if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, lane);
+    load_cv(c, cvb + (size_t)d.nsteps * cv_stride);
+    for (int n = d.nsteps - 1; n >= 0; --n) {
+      double gK[QGD_MAX_M * (QGD_MAX_OPS - 1)], gS[QGD_MAX_M * (QGD_MAX_OPS - 1)];
+      Vec<EL> w0;
+      // ---- implicit side: time level n+1 (its control values are the ones currently loaded)
+      for (int i = 0; i < m * (QGD_MAX_OPS - 1); ++i) { gK[i] = 0.0; gS[i] = 0.0; }
+      adj_sweep<EL, true>(c, lam, a_imp, w0, hist + slot_sz * (n + 1), gK, gS);
+      for (int r = 0; r < m; ++r)
+        for (int k = 0; k < d.Nc; ++k) {
+          const double sK = warp_sum(gK[r * (QGD_MAX_OPS - 1) + k]), sS = warp_sum(gS[r * (QGD_MAX_OPS - 1) + k]);
+          if (lane == 0) { gKs[r * (QGD_MAX_OPS - 1) + k] = sK; gSs[r * (QGD_MAX_OPS - 1) + k] = sS; }
+        }
+      __syncwarp();
+      accumulate_grad(c, ctrls, d.table + (size_t)(n + 1) * tab_stride, gKs, gSs, gacc);
+      __syncwarp();
+      // ---- explicit side: time level n
+      load_cv(c, cvb + (size_t)n * cv_stride);
+      for (int i = 0; i < m * (QGD_MAX_OPS - 1); ++i) { gK[i] = 0.0; gS[i] = 0.0; }
+      Vec<EL> rhs;
+      adj_sweep<EL, true>(c, lam, d.a_rhs, rhs, hist + slot_sz * n, gK, gS);  // rhs = R(t_n)^T lambda_{n+1}
+      for (int r = 0; r < m; ++r)
+        for (int k = 0; k < d.Nc; ++k) {
+          const double sK = warp_sum(gK[r * (QGD_MAX_OPS - 1) + k]), sS = warp_sum(gS[r * (QGD_MAX_OPS - 1) + k]);
+          if (lane == 0) { gKs[r * (QGD_MAX_OPS - 1) + k] = sK; gSs[r * (QGD_MAX_OPS - 1) + k] = sS; }
+        }
+      __syncwarp();
+      accumulate_grad(c, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
+      __syncwarp();
+      if (n >= 1) {
+        // guard forcing f_n = -(2 dt/tf) W w_n   (interior point: trapezoid weight 1)
+        Vec<EL> Ww;
+        vload(w0, hist + slot_sz * n, N, lane);
+        vstore(w0, c.wv, N, lane);
+        __syncwarp();
+        guard_apply(c, c.wv, Ww);
+        vaxpy(rhs, -2.0 * d.dt / d.tf, Ww);
+        // x0 = lambda_{n+1} (forward_evolution.jl:450)
+        const int it = gmres_warp<EL>(c, op, lam, rhs, d.abstol, -1.0, N2, N2, 1);
+        if (lam0) vstore(lam, lam0 + (size_t)N2 * n, N, lane);
+        if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
+      }
+    }
+    __syncwarp();
+    for (int t = lane; t < P; t += 32) a.gradcol[(size_t)t + (size_t)P * ((size_t)cl + (size_t)d.ncol * b)] = gacc[t];
+    __syncwarp();
+  }
+}
+
+// K2 on its own (tests): uv [2N][1+m][ncols]; forward Taylor columns or Lambda_j = W_j^T x.
+template <int EL>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_derivs(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a, double* uv, int ncols,
+                                                                     const double* cv, int adjoint) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (d.ops_in_smem) stage_blob(smem + 16, d.blob, d.lay.bytes, reinterpret_cast<unsigned long long*>(smem));
+  WarpCtx c = make_ctx(d, a, smem);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2, m = d.m;
+  load_cv(c, cv);
+  for (int col = blockIdx.x * wpc + warp; col < ncols; col += gridDim.x * wpc) {
+    double* slot = uv + (size_t)N2 * (m + 1) * col;
+    Vec<EL> x, out, guess;
+    vload(x, slot, N, lane);
+    if (!adjoint) {
+      fwd_derivs<EL, true>(c, x, d.a_rhs, out, &guess, slot);
+    } else {
+      for (int j = 1; j <= m; ++j) {  // Lambda_j = W_j^T x: reverse sweep with alpha = e_j
+        double alpha[QGD_MAX_M + 1];
+        for (int i = 0; i <= m; ++i) alpha[i] = (i == j) ? 1.0 : 0.0;
+        adj_sweep<EL, false>(c, x, alpha, out, nullptr, nullptr, nullptr);
+        vstore(out, slot + (size_t)j * N2, N, lane);
+      }
+    }
+  }
+}
+
+// lambda_history Taylor columns for API fidelity (reference stores Lambda_j of slot n computed with
+// the controls of t_{n-1}, slot 1 with t_1; never read by the gradient -- SURVEY A.5).
+template <int EL>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_lambda_columns(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
+                                                                             double* lam_hist /*[2N][1+m][Nt][ncol][B]*/) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (d.ops_in_smem) stage_blob(smem + 16, d.blob, d.lay.bytes, reinterpret_cast<unsigned long long*>(smem));
+  WarpCtx c = make_ctx(d, a, smem);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2, m = d.m, Nt = d.nsteps + 1;
+  const size_t cv_stride = (size_t)2 * (m + 1) * d.Nc;
+  const size_t slot_sz = (size_t)N2 * (m + 1);
+  const size_t items = (size_t)a.B * d.ncol * Nt;
+  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+    const int n = (int)(item % Nt);
+    const size_t bc = item / Nt;  // cl + ncol*b
+    const int b = (int)(bc / d.ncol);
+    double* slot = lam_hist + slot_sz * ((size_t)n + (size_t)Nt * bc);
+    Vec<EL> x, out;
+    vzero(x);
+    if (n >= 1) vload(x, a.lambda0 + (size_t)N2 * ((size_t)n + (size_t)Nt * bc), N, lane);
+    vstore(x, slot, N, lane);
+    const bool derivs = (n >= 1) && !(n == d.nsteps && d.nsteps == 1 && false);
+    // slot N keeps zero derivative columns only when nsteps == 1 (the loop n = nsteps..2 is empty,
+    // forward_evolution.jl:414,421) -- then slot 1 == slot N is overwritten by the final block (:472-480).
+    const int tn = (n >= 2) ? n - 1 : 1;
+    if (derivs) {
+      load_cv(c, a.cvals + ((size_t)b * Nt + tn) * cv_stride);
+      for (int j = 1; j <= m; ++j) {
+        double alpha[QGD_MAX_M + 1];
+        for (int i = 0; i <= m; ++i) alpha[i] = (i == j) ? 1.0 : 0.0;
+        adj_sweep<EL, false>(c, x, alpha, out, nullptr, nullptr, nullptr);
+        vstore(out, slot + (size_t)j * N2, N, lane);
+      }
+    } else {
+      vzero(out);
+      for (int j = 1; j <= m; ++j) vstore(out, slot + (size_t)j * N2, N, lane);
+    }
+  }
+}
+
+}  // namespace qgd

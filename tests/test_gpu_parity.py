@@ -1,0 +1,235 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same inputs.
+
+Bar: infidelity, gradient and final state within 1e-10 relative, equal GMRES
+iteration counts, with gmres_abstol <= 1e-13 for the parity runs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _cases(q):
+    c = {}
+    c["cnot2"] = q.configs.cnot2(nsteps=20, tf=20.0, gmres_tol=1e-14)
+    c["cnot3_333"] = q.configs.cnot3(nsteps=12, tf=12.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=6)
+    c["cnot3_444_short"] = q.configs.cnot3(nsteps=6, tf=6.0, gmres_tol=1e-14)
+    prob, controls, pcof, target, order = q.configs.dense_random(N=6, Nc=2, nsteps=8, order=10, gmres_tol=1e-14, dt_norm=0.5)
+    c["dense_o10"] = (prob, controls, pcof, target, order)
+    rabi = q.construct_rabi_prob(tf=np.pi, gmres_abstol=1e-15, gmres_reltol=1e-15, nsteps=10)
+    ctl = q.CarrierControl(q.FortranBSplineControl(16, 20, rabi.tf), [-10, -1, 0, 1, 10])
+    rng = np.random.default_rng(0)
+    c["rabi_carrier"] = (rabi, ctl, rng.random(ctl.N_coeff), rng.random((2, 2)) + 1j * rng.random((2, 2)), 8)
+    rnd = q.construct_rand_prob(4, 1, tf=1.0, nsteps=10, gmres_abstol=1e-15, gmres_reltol=1e-15)
+    g = q.GRAPEControl(5, rnd.tf)
+    c["rand_grape"] = (rnd, g, rng.random(g.N_coeff), rng.random((4, 4)) + 1j * rng.random((4, 4)), 6)
+    return c
+
+
+CASE_NAMES = ["cnot2", "cnot3_333", "cnot3_444_short", "dense_o10", "rabi_carrier", "rand_grape"]
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_control_table_vs_oracle(q, O, name):
+    """K1: fill_p_mat!/fill_q_mat! values and eval_grad_* tables vs the oracle, <= 1e-13."""
+    prob, controls, pcof, target, order = _cases(q)[name]
+    h = q.Handle(prob, controls)
+    m = order // 2
+    times = np.linspace(0.0, prob.tf, 7)
+    p, qq, gp, gq = h.eval_controls(pcof, times, m + 1, want_grad=True)
+    sl = q.control_slices(controls)
+    for it, t in enumerate(times):
+        P_, Q_ = O.fill_pq_mat(prob, controls, pcof, t, m + 1)
+        scale = max(1.0, np.abs(P_).max(), np.abs(Q_).max())
+        assert np.abs(p[:, :, it] - P_).max() <= 1e-13 * scale
+        assert np.abs(qq[:, :, it] - Q_).max() <= 1e-13 * scale
+        for k in range(prob.N_operators):
+            for r in range(m + 1):
+                _, _, gpo, gqo = O.eval_pq_derivative(prob, controls, k, pcof[sl[k][0]:sl[k][1]], t, r)
+                s = max(1.0, np.abs(gpo).max(), np.abs(gqo).max())
+                assert np.abs(gp[sl[k][0]:sl[k][1], r, it] - gpo).max() <= 1e-13 * s
+                assert np.abs(gq[sl[k][0]:sl[k][1], r, it] - gqo).max() <= 1e-13 * s
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["cnot3_333", "dense_o10", "rand_grape"])
+def test_taylor_derivative_kernel_vs_oracle(q, O, name):
+    """K2: fused Taylor recursion (all orders) and its transposed sweep vs compute_derivatives! /
+    compute_adjoint_derivatives! of the oracle."""
+    prob, controls, pcof, target, order = _cases(q)[name]
+    h = q.Handle(prob, controls)
+    m = order // 2
+    rng = np.random.default_rng(1)
+    cre = rng.standard_normal((m + 1, prob.N_operators))
+    cim = rng.standard_normal((m + 1, prob.N_operators))
+    ncols = 5
+    uv = np.zeros((prob.real_system_size, m + 1, ncols), order="F")
+    uv[:, 0, :] = rng.standard_normal((prob.real_system_size, ncols))
+    for adjoint in (False, True):
+        out = h.compute_derivatives(uv, order, cre, cim, adjoint=adjoint)
+        for c in range(ncols):
+            ref = O.compute_derivatives(prob, controls, uv[:, :, c], order, cre, cim, adjoint=adjoint)
+            for j in range(m + 1):
+                assert rel(out[:, j, c], ref[:, j]) < 1e-12, (adjoint, j)
+    h.close()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_forward_sweep_parity(q, O, name):
+    prob, controls, pcof, target, order = _cases(q)[name]
+    h = q.Handle(prob, controls)
+    out = h.eval_forward(pcof, order=order)
+    ref_h, ref_it = O.eval_forward(prob, controls, pcof, order=order)
+    assert np.array_equal(out["iters"][:, :, 0], ref_it), "GMRES iteration counts differ"
+    assert rel(out["final_state"][:, :, 0], ref_h[:, 0, -1, :]) < RTOL
+    for j in range(order // 2 + 1):
+        assert rel(out["history"][:, j, :, :, 0], ref_h[:, j]) < RTOL
+    h.close()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_gradient_parity(q, O, name):
+    prob, controls, pcof, target, order = _cases(q)[name]
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_history=True, want_lambda=True,
+                             want_forcing=True, want_iters=True)
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert np.array_equal(out["iters_fwd"][:, :, 0], ref["iters_fwd"])
+    assert np.array_equal(out["iters_term"][:, 0], ref["iters_term"])
+    assert np.array_equal(out["iters_adj"][:, :, 0], ref["iters_adj"])
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+    assert abs(out["guard_penalty"][0] - ref["guard_penalty"]) <= RTOL * max(abs(ref["guard_penalty"]), 1e-300)
+    assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+    assert rel(out["history"][..., 0], ref["history"]) < RTOL
+    assert rel(out["adjoint_forcing"][..., 0], ref["adjoint_forcing"]) < RTOL or not ref["adjoint_forcing"].any()
+    # lambda itself (Taylor column 0) is what the gradient consumes; the derivative columns are API fidelity
+    assert rel(out["lambda_history"][:, 0, :, :, 0], ref["lambda_history"][:, 0]) < 1e-9
+    assert rel(out["lambda_history"][..., 0], ref["lambda_history"]) < 1e-8
+    h.close()
+
+
+@pytest.mark.parametrize("precond", ["identity", "lu", "diagonal"])
+def test_preconditioners(q, O, precond):
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
+    prob.preconditioner_type = {"identity": q.IdentityPreconditioner, "lu": q.LUPreconditioner,
+                                "diagonal": q.DiagonalHamiltonianPreconditioner}[precond]
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert np.array_equal(out["iters_fwd"][:, :, 0], ref["iters_fwd"])
+    assert np.array_equal(out["iters_adj"][:, :, 0], ref["iters_adj"])
+    assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+    h.close()
+
+
+def test_batch_equals_individual(q, O):
+    """Independent control vectors in one launch give the same numbers as one at a time."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
+    P = len(pcof)
+    pcs = np.stack([q.configs.cnot3_pcof(P, s) for s in range(5)], axis=1)
+    h = q.Handle(prob, controls)
+    tgt = q.complex_to_real(target)
+    batch = h.discrete_adjoint(pcs, tgt, order=order)
+    for b in range(pcs.shape[1]):
+        one = h.discrete_adjoint(pcs[:, b], tgt, order=order)
+        assert np.array_equal(one["grad"][:, 0], batch["grad"][:, b])
+        assert one["infidelity"][0] == batch["infidelity"][b]
+        assert one["guard_penalty"][0] == batch["guard_penalty"][b]
+    ref = O.discrete_adjoint(prob, controls, pcs[:, 3], target, order=order)
+    assert rel(batch["grad"][:, 3], ref["grad"]) < RTOL
+    h.close()
+
+
+def test_column_sharding_two_phase(q, O):
+    """Column-sharded two-phase evaluation (what each rank of a multi-GPU job runs) reproduces the
+    all-columns result: gradient partials sum to the full gradient, infidelity identical."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
+    tgt = q.complex_to_real(target)
+    full = q.Handle(prob, controls).discrete_adjoint(pcof, tgt, order=order)
+    nic = prob.N_initial_conditions
+    shards = [(0, 3), (3, 3), (6, 2)]
+    hs, finals, guards = [], [], []
+    for c0, cn in shards:
+        h = q.Handle(prob, controls)
+        h.set_column_shard(c0, cn)
+        f, g = h.adjoint_phase1(pcof, order)
+        hs.append(h); finals.append(f); guards.append(g)
+    final_all = np.concatenate(finals, axis=1)
+    assert final_all.shape[1] == nic
+    grad = 0
+    for h in hs:
+        g, infid = h.adjoint_phase2(tgt, final_all)
+        grad = grad + g
+        assert abs(infid[0] - full["infidelity"][0]) <= 1e-14
+    assert rel(grad[:, 0], full["grad"][:, 0]) < 1e-12
+    assert abs(sum(g[0] for g in guards) - full["guard_penalty"][0]) <= 1e-13 * max(1.0, full["guard_penalty"][0])
+
+
+def test_history_precomputed_and_python_api(q, O):
+    prob, controls, pcof, target, order = q.configs.cnot2(nsteps=16, tf=16.0, gmres_tol=1e-14)
+    g1 = q.discrete_adjoint(prob, controls, pcof, target, order=order)
+    hist = q.eval_forward(prob, controls, pcof, order=order)  # complex [N, 1+nsteps, nic]
+    g2 = np.zeros_like(g1)
+    q.discrete_adjoint_(g2, None, None, None, prob, controls, pcof, target, order=order, history_precomputed=True)
+    assert np.array_equal(g1, g2)
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert rel(g1, ref["grad"]) < RTOL
+    assert rel(hist[:, -1, :], q.real_to_complex(ref["final_state"])) < RTOL
+    assert abs(q.infidelity(prob, controls, pcof, target, order=order) - ref["infidelity"]) <= RTOL * ref["infidelity"]
+    # mutable knobs follow the reference's in-place mutation of prob
+    prob.nsteps = 8
+    ref8 = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert rel(q.discrete_adjoint(prob, controls, pcof, target, order=order), ref8["grad"]) < RTOL
+
+
+def test_save_every_nsteps(q, O):
+    prob, controls, pcof, target, order = q.configs.cnot2(nsteps=12, tf=12.0, gmres_tol=1e-14)
+    h = q.Handle(prob, controls)
+    out = h.eval_forward(pcof, order=order, save_every=3)
+    ref, _ = O.eval_forward(prob, controls, pcof, order=order, saveEveryNsteps=3)
+    assert out["history"].shape[2] == 5
+    assert rel(out["history"][..., 0], ref) < RTOL
+    h.close()
+
+
+def test_full_cnot3_order8(q, O):
+    """BASELINE C2 at full size (N=64, nic=8, nsteps=550, order 8, P=180), parity run at abstol 1e-14."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=550, tf=550.0, gmres_tol=1e-14)
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    mism_f = int((out["iters_fwd"][:, :, 0] != ref["iters_fwd"]).sum())
+    mism_a = int((out["iters_adj"][:, :, 0] != ref["iters_adj"]).sum())
+    print("C2 full: fwd iters total", int(ref["iters_fwd"].sum()), "adj", int(ref["iters_adj"].sum()), "mismatching solves",
+          mism_f, mism_a, "grad rel", rel(out["grad"][:, 0], ref["grad"]))
+    assert mism_f == 0 and mism_a == 0
+    assert np.array_equal(out["iters_term"][:, 0], ref["iters_term"])
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+    assert abs(out["guard_penalty"][0] - ref["guard_penalty"]) <= RTOL * abs(ref["guard_penalty"])
+    assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+    h.close()
+
+
+def test_linearity_of_adjoint_operator_property(q):
+    """Size-independent property at full C2 size: the transposed sweep is the exact transpose of the
+    forward Taylor recursion: <W_j x, y> == <x, W_j^T y> for every order j."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=550, tf=550.0)
+    h = q.Handle(prob, controls)
+    m = order // 2
+    rng = np.random.default_rng(3)
+    cre = 0.05 * rng.standard_normal((m + 1, 3)); cim = 0.05 * rng.standard_normal((m + 1, 3))
+    n2 = prob.real_system_size
+    x = np.zeros((n2, m + 1, 1), order="F"); y = np.zeros((n2, m + 1, 1), order="F")
+    x[:, 0, 0] = rng.standard_normal(n2); y[:, 0, 0] = rng.standard_normal(n2)
+    Wx = h.compute_derivatives(x, order, cre, cim, adjoint=False)
+    WTy = h.compute_derivatives(y, order, cre, cim, adjoint=True)
+    for j in range(1, m + 1):
+        a = float(Wx[:, j, 0] @ y[:, 0, 0]); b = float(x[:, 0, 0] @ WTy[:, j, 0])
+        assert abs(a - b) <= 1e-12 * max(abs(a), abs(b), 1e-3)
+    h.close()
