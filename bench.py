@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("QGD_BENCH_BATCH", "444")),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("QGD_BENCH_BATCH", "296")),
                     help="control vectors per GPU per step")
     ap.add_argument("--nsteps", type=int, default=550)
     ap.add_argument("--shard", default="pcof", choices=["pcof", "columns"])
