@@ -199,6 +199,7 @@ typedef struct qgd_stats {
   double last_forward_ms;  /* CUDA-event time of the forward sweep kernel  */
   double last_backward_ms; /* CUDA-event time of the backward sweep kernel */
   double last_total_ms;    /* CUDA-event time of the whole device section  */
+  int64_t fast_path_launches; /* sweep launches that took the register-operator kernels (qgd_fast.cuh) */
 } qgd_stats_t;
 int qgd_get_stats(qgd_handle_t *h, qgd_stats_t *out);
 

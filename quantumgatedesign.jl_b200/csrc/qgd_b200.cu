@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -251,6 +252,24 @@ void validate_and_load(qgd_handle* h, const qgd_problem_t* p) {
       }
   }
 
+  // ---- does the problem have the structure of the register-operator fast path?  diagonal drift, <= 2 entries per
+  // row and control operator, diagonal guard projector, N <= 64 (qgd_fast.cuh)
+  {
+    bool ok = n <= 64 && h->Nc >= 1 && L.L[0] <= 1 && LW <= 1 && getenv("QGD_DISABLE_FAST") == nullptr;
+    for (int k = 1; k < L.n_ops && ok; ++k) ok = L.L[k] <= 2;
+    if (ok && L.L[0] == 1) {
+      const int* col = reinterpret_cast<const int*>(h->blob.data() + L.off_col[0]);
+      const double* vs = reinterpret_cast<const double*>(h->blob.data() + L.off_vs[0]);
+      for (int r = 0; r < n && ok; ++r) ok = col[r] == r && vs[r] == 0.0;
+    }
+    if (ok && LW == 1) {
+      const int* col = reinterpret_cast<const int*>(h->blob.data() + L.off_wcol);
+      for (int r = 0; r < n2 && ok; ++r) ok = col[r] == r;
+    }
+    h->fast_ok = ok;
+    h->fast_el = n <= 32 ? 1 : 2;
+  }
+
   // ---- upload the static parts
   h->d_u0.reserve((size_t)n * h->nic * 8); h->d_v0.reserve((size_t)n * h->nic * 8);
   CUDA_CHECK(cudaMemcpy(h->d_u0.p, p->u0, (size_t)n * h->nic * 8, cudaMemcpyHostToDevice));
@@ -422,6 +441,36 @@ void iters_out(qgd_handle* h, int64_t* dst, DevBuf& src, size_t n) {  // device 
 
 void reset_stats(qgd_handle* h) { h->stats = qgd_stats_t{}; }
 
+// ---- register-operator fast path dispatch (false: shape not built / not applicable -> generic kernels)
+bool fast_applicable(const qgd_handle* h, int m) {
+  return h->fast_ok && h->precond != QGD_PRECOND_LU && m >= 1 && m <= QGD_FAST_MAX_M;
+}
+#define QGD_FAST_SWITCH(m, NAME, ...)                   \
+  bool done_ = false;                                   \
+  switch (m) {                                          \
+    case 1: done_ = NAME##_m1(__VA_ARGS__); break;      \
+    case 2: done_ = NAME##_m2(__VA_ARGS__); break;      \
+    case 3: done_ = NAME##_m3(__VA_ARGS__); break;      \
+    case 4: done_ = NAME##_m4(__VA_ARGS__); break;      \
+    case 5: done_ = NAME##_m5(__VA_ARGS__); break;      \
+    case 6: done_ = NAME##_m6(__VA_ARGS__); break;      \
+    default: break;                                     \
+  }                                                     \
+  if (done_) h->stats.fast_path_launches++;             \
+  return done_;
+bool try_forward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  if (!fast_applicable(h, d.m)) return false;
+  QGD_FAST_SWITCH(d.m, launch_forward_fast, h, d, a, h->fast_el, h->Nc)
+}
+bool try_backward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  if (!fast_applicable(h, d.m)) return false;
+  QGD_FAST_SWITCH(d.m, launch_backward_fast, h, d, a, h->fast_el, h->Nc)
+}
+bool try_derivs_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a, double* uv, int ncols, const double* cv, int adjoint) {
+  if (!fast_applicable(h, d.m)) return false;
+  QGD_FAST_SWITCH(d.m, launch_derivs_fast, h, d, a, h->fast_el, h->Nc, uv, ncols, cv, adjoint)
+}
+
 // forward sweep on device for B control vectors already in d_pcof
 void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t save_every, bool want_iters) {
   check_order(order);
@@ -443,7 +492,7 @@ void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t 
   a.final_state = h->d_final.as<double>();
   if (want_iters) { h->d_iters_f.reserve((size_t)h->nsteps * h->ncol * B * 4); a.iters = h->d_iters_f.as<int>(); }
   CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
-  QGD_DISPATCH_EL(el, launch_forward, h, d, a);
+  if (!try_forward_fast(h, d, a)) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
   CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
   h->hist_B = B; h->hist_order = order; h->hist_nsteps = h->nsteps; h->hist_save = save_every; h->hist_valid = true;
 }
@@ -494,7 +543,7 @@ void run_adjoint(qgd_handle* h, int B, int order, const double* d_target, bool w
   h->d_gradcol.reserve((size_t)std::max(h->P, 1) * h->ncol * B * 8);
   a.gradcol = h->d_gradcol.as<double>();
   CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
-  QGD_DISPATCH_EL(el, launch_backward, h, d, a);
+  if (!try_backward_fast(h, d, a)) { QGD_DISPATCH_EL(el, launch_backward, h, d, a); }
   CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
   const size_t tot = std::max<size_t>((size_t)h->P * B, (size_t)B);
   k_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->P, h->ncol, B, h->d_gradcol.as<double>(),
@@ -832,7 +881,7 @@ int qgd_compute_derivatives(qgd_handle_t* h, double* uv, int64_t ncols_in, int32
       }
     CUDA_CHECK(cudaMemcpyAsync(d_cv, cv.data(), cv.size() * 8, cudaMemcpyHostToDevice, h->stream));
     SweepArgs a{};
-    QGD_DISPATCH_EL(el, launch_derivs, h, d, a, d_uv, (int)ncols_in, d_cv, adjoint);
+    if (!try_derivs_fast(h, d, a, d_uv, (int)ncols_in, d_cv, adjoint)) { QGD_DISPATCH_EL(el, launch_derivs, h, d, a, d_uv, (int)ncols_in, d_cv, adjoint); }
     CUDA_CHECK(cudaMemcpyAsync(uv, d_uv, sz, cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   });

@@ -1,0 +1,664 @@
+// qgd_fast.cuh -- register-resident-operator sweep kernels (sm_100a): the hot path for the problems the
+// reference is built around (DispersiveProblem-style: diagonal drift, control operators with at most two
+// entries per row such as a +- a^dagger, diagonal guard projector, Identity or DiagonalHamiltonian
+// preconditioner, N_tot_levels <= 64).  Everything else runs on the generic kernels of qgd_kernels.cuh.
+//
+// One warp = one initial-condition column of one control vector, marching all time steps on-device.
+//   * Hamiltonian blocks live in REGISTERS (values + gather columns of the <= 2 entries per row and
+//     operator), the state is exchanged between lanes through a 16-byte (u,v)-interleaved shared-memory
+//     buffer (one LDS.128 per gathered entry).
+//   * Taylor recursion in scatter form: the sparse products K_k w_i, S_k w_i are formed ONCE per Taylor
+//     column (m sparse sweeps per operator evaluation instead of m(m+1)/2) and immediately scattered
+//     into all later columns with the control Taylor coefficients (compute_derivatives!, reference
+//     src/hermite.jl:56-101; apply_hamiltonian!, :556-588).
+//   * GMRES (IterativeSolvers.jl semantics): Krylov basis in shared memory (first KS
+//     vectors) with an L2-resident tail that is prefetched one vector ahead; modified Gram-Schmidt dot
+//     products reduced across the warp either by the 5-stage shuffle butterfly or by two FP64 tensor-core
+//     DMMA.8x8x4 with a ones operand (measured 66 vs 175 cycles, profiles/r01_microbench.txt); Givens
+//     rotations applied progressively to each new Hessenberg column (same rotations in the same order as
+//     solve_least_squares!, so same numbers), triangular solve from the packed R factor.
+#pragma once
+#include "qgd_kernels.cuh"
+
+namespace qgd {
+
+#ifndef QGD_FAST_RED
+#define QGD_FAST_RED 1  // 0: shuffle butterfly, 1: DMMA ones-matrix all-reduce
+#endif
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+// Sum of one double per lane, result in every lane.
+__device__ __forceinline__ double warp_allsum(double p) {
+#if QGD_FAST_RED == 1
+  // B operand (4x8, lane l <-> B[l%4][l/4]) = p, A = ones: D[i][j] = sum of the 4 lanes of group j; lane l
+  // receives groups 2(l%4), 2(l%4)+1.  Their sum as A operand (8x4, lane l <-> A[l/4][l%4]) times ones
+  // gives the total in every lane.
+  double c0, c1, t0, t1;
+  dmma884(c0, c1, 1.0, p);
+  dmma884(t0, t1, c0 + c1, 1.0);
+  return t0;
+#else
+  return warp_sum(p);
+#endif
+}
+
+template <int EL>
+__device__ __forceinline__ double vdot_local(const Vec<EL>& a, const Vec<EL>& b) {
+  double s0 = a.u[0] * b.u[0], s1 = a.v[0] * b.v[0];
+#pragma unroll
+  for (int e = 1; e < EL; ++e) { s0 = fma(a.u[e], b.u[e], s0); s1 = fma(a.v[e], b.v[e], s1); }
+  return s0 + s1;
+}
+
+// ---- per-lane operator registers ---------------------------------------------------------------------
+template <int EL, int NC>
+struct RegOps {
+  double kd[EL];            // drift: diagonal of K_s (an antisymmetric S_s has a zero diagonal)
+  int col[EL][NC][2];       // gather column of entry s of row (lane + 32 e) of control operator k
+  double vk[EL][NC][2];     // K_c value
+  double vs[EL][NC][2];     // S_c value
+  double pr_ratio[EL], pr_up[EL], pr_den[EL], pr_dg[EL];  // DiagonalHamiltonianPreconditioner
+  double wu[EL], wv[EL];    // guard projector diagonal (u rows, v rows)
+};
+
+template <int EL, int NC>
+__device__ __forceinline__ void load_regops(RegOps<EL, NC>& R, const QgdDevProb& d, int lane, int dir) {
+  const QgdOpLayout& L = d.lay;
+  const int N = d.N;
+#pragma unroll
+  for (int e = 0; e < EL; ++e) {
+    const int r = lane + 32 * e;
+    const bool ok = r < N;
+    R.kd[e] = (ok && L.L[0] > 0) ? reinterpret_cast<const double*>(d.blob + L.off_vk[0])[r] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int* col = reinterpret_cast<const int*>(d.blob + L.off_col[k + 1]);
+      const double* vk = reinterpret_cast<const double*>(d.blob + L.off_vk[k + 1]);
+      const double* vs = reinterpret_cast<const double*>(d.blob + L.off_vs[k + 1]);
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const bool have = ok && s < L.L[k + 1];
+        R.col[e][k][s] = have ? col[s * N + r] : 0;
+        R.vk[e][k][s] = have ? vk[s * N + r] : 0.0;
+        R.vs[e][k][s] = have ? vs[s * N + r] : 0.0;
+      }
+    }
+    if (d.precond == QGD_PRECOND_DIAGONAL && dir >= 0) {
+      const double* pd = reinterpret_cast<const double*>(d.blob + L.off_pre[dir]);
+      R.pr_dg[e] = ok ? pd[r] : 1.0;
+      R.pr_up[e] = ok ? pd[d.N2 + r] : 0.0;
+      R.pr_ratio[e] = ok ? pd[d.N2 + N + r] : 0.0;
+      R.pr_den[e] = ok ? pd[d.N2 + 2 * N + r] : 1.0;
+    } else {
+      R.pr_dg[e] = 1.0; R.pr_up[e] = 0.0; R.pr_ratio[e] = 0.0; R.pr_den[e] = 1.0;
+    }
+    if (L.LW > 0 && ok) {
+      const double* wv = reinterpret_cast<const double*>(d.blob + L.off_wval);
+      R.wu[e] = wv[r]; R.wv[e] = wv[N + r];
+    } else {
+      R.wu[e] = 0.0; R.wv[e] = 0.0;
+    }
+  }
+}
+
+// ---- per-warp context ----------------------------------------------------------------------------------
+template <int EL>
+struct FastCtx {
+  int lane, N, N2, KS;
+  double2* xs;    // smem [2][32*EL]   (u,v) gather buffers (double buffered)
+  double2* cv;    // smem [M+1][NC]    (p_k^(d)/d!, q_k^(d)/d!) of the current time level
+  double* nullv;  // smem [N2+2]       left null vector of the residual recurrence
+  double2* rot;   // smem [N2+2]       Givens (cs, sn)
+  double* g;      // smem [N2+2]       rotated right-hand side, then the least-squares solution
+  double2* Vs;    // smem [KS][32*EL]  Krylov basis, resident part
+  double2* Vg;    // global            Krylov basis, tail (vector i >= KS at (i-KS)*32*EL)
+  double* Rg;     // global            packed upper-triangular R: column j at j(j+1)/2
+};
+template <int EL, int M, int NC>
+__host__ __device__ constexpr int fast_fixed_doubles(int N2) {
+  // xs + cv + nullv + rot + g
+  return 2 * 2 * 32 * EL + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2) + (N2 + 2);
+}
+
+template <int EL>
+__device__ __forceinline__ void xs_store(double2* xs, const Vec<EL>& a, int lane) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) xs[lane + 32 * e] = make_double2(a.u[e], a.v[e]);
+}
+template <int EL>
+__device__ __forceinline__ void v2_load(Vec<EL>& a, const double2* p, int lane) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) { const double2 t = p[lane + 32 * e]; a.u[e] = t.x; a.v[e] = t.y; }
+}
+template <int EL>
+__device__ __forceinline__ void v2_load_cg(Vec<EL>& a, const double2* p, int lane) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) { const double2 t = __ldcg(p + lane + 32 * e); a.u[e] = t.x; a.v[e] = t.y; }
+}
+template <int EL>
+__device__ __forceinline__ void v2_store(double2* p, const Vec<EL>& a, int lane) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) p[lane + 32 * e] = make_double2(a.u[e], a.v[e]);
+}
+
+// z-sums of one vector (in the gather buffer): K_k x and S_k x restricted to this lane's rows.
+template <int EL, int NC>
+struct ZS { double Ku[EL][NC], Kv[EL][NC], Su[EL][NC], Sv[EL][NC]; };
+
+template <int EL, int NC>
+__device__ __forceinline__ void zsums(const RegOps<EL, NC>& R, const double2* xs, ZS<EL, NC>& z) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const double2 g0 = xs[R.col[e][k][0]], g1 = xs[R.col[e][k][1]];
+      z.Ku[e][k] = fma(R.vk[e][k][1], g1.x, R.vk[e][k][0] * g0.x);
+      z.Kv[e][k] = fma(R.vk[e][k][1], g1.y, R.vk[e][k][0] * g0.y);
+      z.Su[e][k] = fma(R.vs[e][k][1], g1.x, R.vs[e][k][0] * g0.x);
+      z.Sv[e][k] = fma(R.vs[e][k][1], g1.y, R.vs[e][k][0] * g0.y);
+    }
+}
+
+// out = sum_j alpha_j w_j, w_0 = x, w_{j+1} = (1/(j+1)) sum_{i<=j} A_{j-i} w_i  (scatter form).
+// STEP: also guess = sum_j a_tay_j w_j and, if hist != nullptr, hist[:, j] = w_j.
+template <int EL, int M, int NC, bool STEP>
+__device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
+                                         Vec<EL>& out, const double* a_tay, Vec<EL>* guess, double* hist) {
+  const int lane = c.lane, N = c.N, N2 = c.N2;
+  Vec<EL> acc[M + 1];
+#pragma unroll
+  for (int j = 1; j <= M; ++j) vzero(acc[j]);
+  Vec<EL> w = x;
+  out = x;
+  vscale(out, alpha[0]);
+  if (STEP) {
+    *guess = x;
+    if (hist) vstore(x, hist, N, lane);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    if (i > 0) {
+      const double inv = 1.0 / (double)i;
+      w = acc[i];
+      vscale(w, inv);
+      vaxpy(out, alpha[i], w);
+      if (STEP) {
+        vaxpy(*guess, a_tay[i], w);
+        if (hist) vstore(w, hist + (size_t)i * N2, N, lane);
+      }
+    }
+    double2* xb = c.xs + (i & 1) * 32 * EL;
+    xs_store<EL>(xb, w, lane);
+    __syncwarp();
+    ZS<EL, NC> z;
+    zsums<EL, NC>(R, xb, z);
+#pragma unroll
+    for (int j = i; j < M; ++j) {
+      const int dd = j - i;
+#pragma unroll
+      for (int e = 0; e < EL; ++e) {
+        double au = acc[j + 1].u[e], av = acc[j + 1].v[e];
+        if (dd == 0) { au = fma(R.kd[e], w.v[e], au); av = fma(-R.kd[e], w.u[e], av); }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const double2 cc = c.cv[dd * NC + k];
+          au = fma(cc.y, z.Su[e][k], fma(cc.x, z.Kv[e][k], au));
+          av = fma(cc.y, z.Sv[e][k], fma(-cc.x, z.Ku[e][k], av));
+        }
+        acc[j + 1].u[e] = au; acc[j + 1].v[e] = av;
+      }
+    }
+  }
+  {
+    const double inv = 1.0 / (double)M;
+    w = acc[M];
+    vscale(w, inv);
+    vaxpy(out, alpha[M], w);
+    if (STEP) {
+      vaxpy(*guess, a_tay[M], w);
+      if (hist) vstore(w, hist + (size_t)M * N2, N, lane);
+    }
+  }
+}
+
+// Reverse sweep: what_j = alpha_j x; for j = M-1..0: what_{j-d} -= (1/(j+1)) A_d what_{j+1}, d = 0..j.
+// out = what_0 = (sum_j alpha_j W_j)^T x.  GRAD: accumulate per lane
+//   gK[r][k] += IPK_k(w_i, what_{j+1})/(j+1), gS[r][k] += IPS_k(w_i, what_{j+1})/(j+1), r = j - i,
+// with w_i the forward Taylor columns of the same time level (hist, global).  SURVEY A.6.
+template <int EL, int M, int NC, bool GRAD>
+__device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
+                                         Vec<EL>& out, const double* hist, double (&gK)[M][NC], double (&gS)[M][NC]) {
+  const int lane = c.lane, N = c.N, N2 = c.N2;
+  Vec<EL> what[M + 1];
+#pragma unroll
+  for (int j = 0; j <= M; ++j) { what[j] = x; vscale(what[j], alpha[j]); }
+  Vec<EL> wh[M];
+  if (GRAD) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) vload(wh[i], hist + (size_t)i * N2, N, lane);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = M - 1; j >= 0; --j) {
+    double2* xb = c.xs + (j & 1) * 32 * EL;
+    xs_store<EL>(xb, what[j + 1], lane);
+    __syncwarp();
+    ZS<EL, NC> z;
+    zsums<EL, NC>(R, xb, z);
+    const double inv = 1.0 / (double)(j + 1);
+#pragma unroll
+    for (int e = 0; e < EL; ++e) {
+      what[j].u[e] -= inv * (R.kd[e] * what[j + 1].v[e]);
+      what[j].v[e] -= inv * (-R.kd[e] * what[j + 1].u[e]);
+    }
+#pragma unroll
+    for (int dd = 0; dd <= j; ++dd)
+#pragma unroll
+      for (int e = 0; e < EL; ++e) {
+        double au = 0.0, av = 0.0;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const double2 cc = c.cv[dd * NC + k];
+          au = fma(cc.y, z.Su[e][k], fma(cc.x, z.Kv[e][k], au));
+          av = fma(cc.y, z.Sv[e][k], fma(-cc.x, z.Ku[e][k], av));
+        }
+        what[j - dd].u[e] = fma(-inv, au, what[j - dd].u[e]);
+        what[j - dd].v[e] = fma(-inv, av, what[j - dd].v[e]);
+      }
+    if (GRAD) {
+#pragma unroll
+      for (int i = 0; i <= j; ++i) {
+        const int rr = j - i;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          double sK = 0.0, sS = 0.0;
+#pragma unroll
+          for (int e = 0; e < EL; ++e) {
+            sK = fma(wh[i].v[e], z.Ku[e][k], fma(-wh[i].u[e], z.Kv[e][k], sK));
+            sS = fma(wh[i].u[e], z.Su[e][k], fma(wh[i].v[e], z.Sv[e][k], sS));
+          }
+          gK[rr][k] = fma(inv, sK, gK[rr][k]);
+          gS[rr][k] = fma(-inv, sS, gS[rr][k]);
+        }
+      }
+    }
+  }
+  out = what[0];
+}
+
+template <int EL, int NC>
+__device__ __forceinline__ void precond_fast(const RegOps<EL, NC>& R, Vec<EL>& x) {  // preconditioners.jl:108-126
+#pragma unroll
+  for (int e = 0; e < EL; ++e) {
+    double xv = x.v[e] - x.u[e] * R.pr_ratio[e];
+    xv = xv / R.pr_den[e];
+    double xu = x.u[e] - R.pr_up[e] * xv;
+    xu = xu / R.pr_dg[e];
+    x.u[e] = xu; x.v[e] = xv;
+  }
+}
+
+// ---- Krylov basis access: resident part in shared memory, tail in L2 ---------------------------------
+template <int EL>
+__device__ __forceinline__ void basis_load(const FastCtx<EL>& c, int i, Vec<EL>& a) {
+  if (i < c.KS) v2_load<EL>(a, c.Vs + (size_t)i * 32 * EL, c.lane);
+  else v2_load_cg<EL>(a, c.Vg + (size_t)(i - c.KS) * 32 * EL, c.lane);
+}
+template <int EL>
+__device__ __forceinline__ void basis_store(const FastCtx<EL>& c, int i, const Vec<EL>& a) {
+  if (i < c.KS) v2_store<EL>(c.Vs + (size_t)i * 32 * EL, a, c.lane);
+  else v2_store<EL>(c.Vg + (size_t)(i - c.KS) * 32 * EL, a, c.lane);
+}
+
+__device__ __forceinline__ int roff(int j) { return (j * (j + 1)) >> 1; }
+
+// Solve R y = g (R upper triangular, packed columns in global memory), y overwrites c.g (shared).
+template <int EL>
+__device__ __forceinline__ void trsv_fast(const FastCtx<EL>& c, int width) {
+  const int lane = c.lane;
+  __syncwarp();
+  for (int j = width - 1; j >= 0; --j) {
+    const double* col = c.Rg + roff(j);
+    const double yj = c.g[j] / __ldcg(col + j);
+    __syncwarp();
+    if (lane == 0) c.g[j] = yj;
+    for (int i = lane; i < j; i += 32) c.g[i] = fma(-yj, __ldcg(col + i), c.g[i]);
+    __syncwarp();
+  }
+}
+
+// GMRES for the time-stepping solves (fixed absolute tolerance, restart = maxiter = 2N).
+// OP: apply(in, out) = A in; left preconditioner applied here.  Returns the number of iterations.
+template <int EL, int NC, class OP>
+__device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
+                          int restart, int maxiter) {
+  const int lane = c.lane;
+  Vec<EL> v, w;
+  op.apply(x, w);
+#pragma unroll
+  for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
+  precond_fast<EL, NC>(R, v);
+  double beta = sqrt(warp_allsum(vdot_local<EL>(v, v)));
+  vscale(v, 1.0 / beta);
+  basis_store<EL>(c, 0, v);
+  double cur = beta, res_beta = beta, accum = 1.0, gcur = beta;
+  __syncwarp();
+  if (lane == 0) c.nullv[0] = 1.0;
+  __syncwarp();
+  int k = 1, it = 0;
+  while (it < maxiter && cur > tol) {
+    op.apply(v, w);  // expand!
+    precond_fast<EL, NC>(R, w);
+    // modified Gram-Schmidt against V[:, 0..k-1]; rotation i-1 is applied to (h_{i-1}, h_i) as soon as h_i exists
+    double dsum = 0.0, hprev = 0.0;
+    double* rcol = c.Rg + roff(k - 1);
+    Vec<EL> vi;
+    basis_load<EL>(c, 0, vi);
+    for (int i = 0; i < k; ++i) {
+      Vec<EL> vn;
+      if (i + 1 < k) basis_load<EL>(c, i + 1, vn);
+      const double h = warp_allsum(vdot_local<EL>(vi, w));
+      vaxpy(w, -h, vi);
+      dsum = fma(c.nullv[i], h, dsum);
+      if (i > 0) {
+        const double2 cs = c.rot[i - 1];
+        const double r = cs.x * hprev + cs.y * h;
+        hprev = -cs.y * hprev + cs.x * h;
+        if (lane == 0) rcol[i - 1] = r;
+      } else {
+        hprev = h;
+      }
+      if (i + 1 < k) vi = vn;
+    }
+    const double nrm = sqrt(warp_allsum(vdot_local<EL>(w, w)));
+    vscale(w, 1.0 / nrm);
+    basis_store<EL>(c, k, w);
+    {  // new rotation (k-1) from (hprev, nrm); update the rotated right-hand side
+      double cs, sn;
+      givens(hprev, nrm, cs, sn);
+      if (lane == 0) {
+        rcol[k - 1] = cs * hprev + sn * nrm;
+        c.rot[k - 1] = make_double2(cs, sn);
+        c.g[k - 1] = cs * gcur;
+      }
+      gcur = -sn * gcur;
+    }
+    const double nv = -(dsum / nrm);  // update_residual!
+    if (lane == 0) c.nullv[k] = nv;
+    accum = fma(nv, nv, accum);
+    cur = res_beta / sqrt(accum);
+    k += 1;
+    v = w;
+    __syncwarp();
+    if (k == restart + 1 || cur <= tol) {
+      const int width = k - 1;
+      trsv_fast<EL>(c, width);
+      basis_load<EL>(c, 0, vi);
+      for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 0..width-1] y
+        Vec<EL> vn;
+        if (j + 1 < width) basis_load<EL>(c, j + 1, vn);
+        vaxpy(x, c.g[j], vi);
+        if (j + 1 < width) vi = vn;
+      }
+      k = 1;
+      if (cur > tol) {  // restart (residual.current keeps its value, as in the package)
+        op.apply(x, w);
+#pragma unroll
+        for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
+        precond_fast<EL, NC>(R, v);
+        beta = sqrt(warp_allsum(vdot_local<EL>(v, v)));
+        vscale(v, 1.0 / beta);
+        basis_store<EL>(c, 0, v);
+        accum = 1.0; res_beta = beta; gcur = beta;
+        __syncwarp();
+        if (lane == 0) c.nullv[0] = 1.0;
+      }
+      __syncwarp();
+    }
+    it += 1;
+  }
+  return it;
+}
+
+template <int EL, int M, int NC>
+struct FwdOpFast {  // LHSHolder (src/forward_evolution.jl:583-592)
+  const FastCtx<EL>& c; const RegOps<EL, NC>& R; const double* a_lhs;
+  __device__ __forceinline__ void apply(const Vec<EL>& in, Vec<EL>& out) const {
+    fwd_fast<EL, M, NC, false>(c, R, in, a_lhs, out, nullptr, nullptr, nullptr);
+  }
+};
+template <int EL, int M, int NC>
+struct AdjOpFast {  // LHSHolderAdjoint (:624-633) through the reverse sweep
+  const FastCtx<EL>& c; const RegOps<EL, NC>& R; const double* a_lhs;
+  __device__ __forceinline__ void apply(const Vec<EL>& in, Vec<EL>& out) const {
+    double dK[M][NC], dS[M][NC];
+    adj_fast<EL, M, NC, false>(c, R, in, a_lhs, out, nullptr, dK, dS);
+  }
+};
+
+// control Taylor coefficients of a time level: global [2][M+1][NC] -> shared (p, q) pairs [M+1][NC]
+template <int EL, int M, int NC>
+__device__ __forceinline__ void load_cv_fast(const FastCtx<EL>& c, const double* src) {
+  __syncwarp();
+  for (int i = c.lane; i < (M + 1) * NC; i += 32) c.cv[i] = make_double2(src[i], src[(M + 1) * NC + i]);
+  __syncwarp();
+}
+
+// shared-memory carve-up: [warp regions]; each region = fixed part + KS basis vectors (+ extra doubles)
+template <int EL, int M, int NC>
+__device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra) {
+  FastCtx<EL> c;
+  c.lane = threadIdx.x & 31;
+  c.N = d.N; c.N2 = d.N2; c.KS = a.ks;
+  const int warp = threadIdx.x >> 5;
+  double* w = reinterpret_cast<double*>(smem) + (size_t)warp * a.warp_smem_doubles;
+  c.xs = reinterpret_cast<double2*>(w); w += 2 * 2 * 32 * EL;
+  c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
+  c.rot = reinterpret_cast<double2*>(w); w += 2 * (d.N2 + 2);
+  c.nullv = w; w += d.N2 + 2;
+  c.g = w; w += d.N2 + 2;
+  c.Vs = reinterpret_cast<double2*>(w); w += (size_t)a.ks * 2 * 32 * EL;
+  *extra = w;
+  const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  c.Vg = reinterpret_cast<double2*>(a.Vws + slot * a.v_stride);
+  c.Rg = a.Hws + slot * a.h_stride;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <int EL, int M, int NC>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* extra;
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2;
+  RegOps<EL, NC> R;
+  load_regops<EL, NC>(R, d, lane, 0);
+  double a_rhs[M + 1], a_lhs[M + 1], a_tay[M + 1];
+#pragma unroll
+  for (int j = 0; j <= M; ++j) { a_rhs[j] = d.a_rhs[j]; a_lhs[j] = d.a_lhs[j]; a_tay[j] = d.a_tay[j]; }
+  const size_t items = (size_t)a.B * d.ncol;
+  const size_t cv_stride = (size_t)2 * (M + 1) * NC;
+  const size_t slot_sz = (size_t)N2 * (M + 1);
+  const FwdOpFast<EL, M, NC> op{c, R, a_lhs};
+  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+    const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
+    const double* cvb = a.cvals + (size_t)b * (d.nsteps + 1) * cv_stride;
+    double* hist = a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b);
+    Vec<EL> x;
+#pragma unroll
+    for (int e = 0; e < EL; ++e) {
+      const int r = lane + 32 * e;
+      x.u[e] = r < N ? d.u0[r + (size_t)N * col] : 0.0;
+      x.v[e] = r < N ? d.v0[r + (size_t)N * col] : 0.0;
+    }
+    load_cv_fast<EL, M, NC>(c, cvb);
+    for (int n = 0; n < d.nsteps; ++n) {
+      Vec<EL> rhs, guess;
+      double* slot = (n % a.save_every == 0) ? hist + slot_sz * (n / a.save_every) : nullptr;
+      fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, rhs, a_tay, &guess, slot);      // explicit part at t_n
+      load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n + 1) * cv_stride);              // implicit part uses t_{n+1}
+      x = guess;
+      const int it = gmres_fast<EL, NC>(c, R, op, x, rhs, d.abstol, N2, N2);
+      if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
+    }
+    {  // Taylor columns at the final time (forward_evolution.jl:232-242)
+      Vec<EL> dummy, guess;
+      double* slot = (d.nsteps % a.save_every == 0) ? hist + slot_sz * (d.nsteps / a.save_every) : nullptr;
+      fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, dummy, a_tay, &guess, slot);
+      vstore(x, a.final_state + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b), N, lane);
+    }
+  }
+}
+
+// grad_acc[theta] -= sum_r table_p[r][theta] gK[r][k(theta)] + table_q[r][theta] gS[r][k(theta)]
+template <int M, int NC>
+__device__ __forceinline__ void accumulate_grad_fast(int lane, int P, const QgdDevControl* ctrls, const double* table_n,
+                                                     const double* gKs, const double* gSs, double* gacc) {
+  const int nd = M + 1;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int off = ctrls[k].offset, nco = ctrls[k].ncoeff;
+    for (int t = lane; t < nco; t += 32) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        s = fma(table_n[((size_t)0 * nd + r) * P + off + t], gKs[r * NC + k], s);
+        s = fma(table_n[((size_t)1 * nd + r) * P + off + t], gSs[r * NC + k], s);
+      }
+      gacc[off + t] -= s;
+    }
+  }
+}
+
+template <int EL, int M, int NC>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
+                                                                               const QgdDevControl* __restrict__ ctrls) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* extra;
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2, Nt = d.nsteps + 1, P = d.P;
+  RegOps<EL, NC> R;
+  load_regops<EL, NC>(R, d, lane, 1);
+  double a_rhs[M + 1], a_lhs[M + 1], a_imp[M + 1];
+#pragma unroll
+  for (int j = 0; j <= M; ++j) { a_rhs[j] = d.a_rhs[j]; a_lhs[j] = d.a_lhs[j]; a_imp[j] = -d.a_lhs[j]; }
+  const size_t items = (size_t)a.B * d.ncol;
+  const size_t cv_stride = (size_t)2 * (M + 1) * NC;
+  const size_t slot_sz = (size_t)N2 * (M + 1);
+  const size_t tab_stride = (size_t)2 * (M + 1) * P;
+  double* gacc = extra;          // [P]
+  double* gKs = gacc + P;        // [M][NC] reduced g^K
+  double* gSs = gKs + M * NC;    // [M][NC] reduced g^S
+  const AdjOpFast<EL, M, NC> op{c, R, a_lhs};
+  const double fsc = -2.0 * d.dt / d.tf;
+  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+    const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
+    const double* cvb = a.cvals + (size_t)b * Nt * cv_stride;
+    const double* hist = a.history + slot_sz * Nt * ((size_t)cl + (size_t)d.ncol * b);
+    double* lam0 = a.lambda0 ? a.lambda0 + (size_t)N2 * Nt * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
+    for (int t = lane; t < P; t += 32) gacc[t] = 0.0;
+    Vec<EL> lam;
+    vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
+    if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, lane);
+    load_cv_fast<EL, M, NC>(c, cvb + (size_t)d.nsteps * cv_stride);
+    for (int n = d.nsteps - 1; n >= 0; --n) {
+      double gK[M][NC], gS[M][NC];
+      Vec<EL> w0, rhs;
+      // ---- implicit side: time level n+1 (its control values are the ones currently loaded)
+#pragma unroll
+      for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) { gK[r][k] = 0.0; gS[r][k] = 0.0; }
+      adj_fast<EL, M, NC, true>(c, R, lam, a_imp, w0, hist + slot_sz * (n + 1), gK, gS);
+#pragma unroll
+      for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const double sK = warp_allsum(gK[r][k]), sS = warp_allsum(gS[r][k]);
+          if (lane == 0) { gKs[r * NC + k] = sK; gSs[r * NC + k] = sS; }
+        }
+      __syncwarp();
+      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)(n + 1) * tab_stride, gKs, gSs, gacc);
+      __syncwarp();
+      // ---- explicit side: time level n
+      load_cv_fast<EL, M, NC>(c, cvb + (size_t)n * cv_stride);
+#pragma unroll
+      for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) { gK[r][k] = 0.0; gS[r][k] = 0.0; }
+      adj_fast<EL, M, NC, true>(c, R, lam, a_rhs, rhs, hist + slot_sz * n, gK, gS);  // rhs = R(t_n)^T lambda_{n+1}
+#pragma unroll
+      for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const double sK = warp_allsum(gK[r][k]), sS = warp_allsum(gS[r][k]);
+          if (lane == 0) { gKs[r * NC + k] = sK; gSs[r * NC + k] = sS; }
+        }
+      __syncwarp();
+      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
+      __syncwarp();
+      if (n >= 1) {
+        // guard forcing f_n = -(2 dt/tf) W w_n (interior point: trapezoid weight 1), W diagonal
+        vload(w0, hist + slot_sz * n, N, lane);
+#pragma unroll
+        for (int e = 0; e < EL; ++e) {
+          rhs.u[e] = fma(fsc, R.wu[e] * w0.u[e], rhs.u[e]);
+          rhs.v[e] = fma(fsc, R.wv[e] * w0.v[e], rhs.v[e]);
+        }
+        // x0 = lambda_{n+1} (forward_evolution.jl:450)
+        const int it = gmres_fast<EL, NC>(c, R, op, lam, rhs, d.abstol, N2, N2);
+        if (lam0) vstore(lam, lam0 + (size_t)N2 * n, N, lane);
+        if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
+      }
+    }
+    __syncwarp();
+    for (int t = lane; t < P; t += 32) a.gradcol[(size_t)t + (size_t)P * ((size_t)cl + (size_t)d.ncol * b)] = gacc[t];
+    __syncwarp();
+  }
+}
+
+// K2 on its own (tests): uv [2N][1+m][ncols]; forward Taylor columns or Lambda_j = W_j^T x.
+template <int EL, int M, int NC>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_derivs_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a, double* uv,
+                                                                             int ncols, const double* cv, int adjoint) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* extra;
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2;
+  RegOps<EL, NC> R;
+  load_regops<EL, NC>(R, d, lane, -1);
+  double a_rhs[M + 1], a_tay[M + 1];
+#pragma unroll
+  for (int j = 0; j <= M; ++j) { a_rhs[j] = d.a_rhs[j]; a_tay[j] = d.a_tay[j]; }
+  load_cv_fast<EL, M, NC>(c, cv);
+  for (int col = blockIdx.x * wpc + warp; col < ncols; col += gridDim.x * wpc) {
+    double* slot = uv + (size_t)N2 * (M + 1) * col;
+    Vec<EL> x, out, guess;
+    vload(x, slot, N, lane);
+    if (!adjoint) {
+      fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, out, a_tay, &guess, slot);
+    } else {
+#pragma unroll
+      for (int j = 1; j <= M; ++j) {  // Lambda_j = W_j^T x: reverse sweep with alpha = e_j
+        double alpha[M + 1];
+#pragma unroll
+        for (int i = 0; i <= M; ++i) alpha[i] = (i == j) ? 1.0 : 0.0;
+        double dK[M][NC], dS[M][NC];
+        adj_fast<EL, M, NC, false>(c, R, x, alpha, out, nullptr, dK, dS);
+        vstore(out, slot + (size_t)j * N2, N, lane);
+      }
+    }
+  }
+}
+
+}  // namespace qgd

@@ -1,0 +1,94 @@
+// qgd_fast_inst.cuh -- launch planning + launchers of the register-operator kernels (qgd_fast.cuh) for one
+// Taylor depth M = order/2.  Included by qgd_fast_m*.cu with QGD_FAST_M defined so that the heavily unrolled
+// kernels compile in parallel translation units.
+#pragma once
+#include "qgd_host.h"
+#include "qgd_fast.cuh"
+
+namespace {
+using namespace qgd;
+
+struct FastCfg { int grid, threads, wpc, ks, warp_doubles; size_t smem; };
+
+// One CTA per SM, all of its shared memory split between the warps; whatever is left after the fixed
+// per-warp arrays holds the resident part of the Krylov basis.
+template <class K>
+FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t items, int extra_doubles, int restart) {
+  const size_t max_smem = h->prop.sharedMemPerBlockOptin;
+  const int sms = h->prop.multiProcessorCount;
+  FastCfg L{};
+  L.wpc = (int)std::min<size_t>(QGD_WARPS_PER_CTA, std::max<size_t>(1, (items + sms - 1) / sms));
+  const int vec = 2 * 32 * el;
+  const int base = (fixed_doubles + extra_doubles + 1) & ~1;
+  const long per_warp = (long)(max_smem / 8 / L.wpc) & ~1L;
+  long ks = (per_warp - base) / vec;
+  ks = std::min<long>(ks, restart + 1);
+  if (ks < 2) throw QgdError(QGD_EUNSUPPORTED, "fast path: shared memory too small for the per-warp state");
+  L.ks = (int)ks;
+  L.warp_doubles = base + (int)ks * vec;
+  L.threads = 32 * L.wpc;
+  L.smem = (size_t)L.wpc * L.warp_doubles * 8;
+  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  const size_t ctas = (items + L.wpc - 1) / L.wpc;
+  L.grid = (int)std::max<size_t>(1, std::min<size_t>(ctas, (size_t)sms));
+  return L;
+}
+
+void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, SweepArgs& a) {
+  const size_t warps = (size_t)L.grid * L.wpc;
+  a.v_stride = (size_t)std::max(restart + 1 - L.ks, 1) * 2 * 32 * el;
+  a.h_stride = (size_t)restart * (restart + 3) / 2 + 2;
+  h->d_V.reserve(warps * a.v_stride * 8);
+  h->d_H.reserve(warps * a.h_stride * 8);
+  a.Vws = h->d_V.as<double>();
+  a.Hws = h->d_H.as<double>();
+  a.ks = L.ks;
+  a.warp_smem_doubles = L.warp_doubles;
+}
+
+template <int EL, int M, int NC>
+void launch_forward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  FastCfg L = plan_fast(h, k_forward_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)a.B * d.ncol, 0, d.N2);
+  ensure_krylov_fast(h, L, EL, d.N2, a);
+  k_forward_fast<EL, M, NC><<<L.grid, L.threads, L.smem, h->stream>>>(d, a);
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+}
+template <int EL, int M, int NC>
+void launch_backward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  const int extra = d.P + 2 * M * NC;
+  FastCfg L = plan_fast(h, k_backward_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)a.B * d.ncol, extra, d.N2);
+  ensure_krylov_fast(h, L, EL, d.N2, a);
+  k_backward_fast<EL, M, NC><<<L.grid, L.threads, L.smem, h->stream>>>(d, a, h->d_ctrls.as<QgdDevControl>());
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+}
+template <int EL, int M, int NC>
+void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, int ncols, const double* cv, int adjoint) {
+  FastCfg L = plan_fast(h, k_derivs_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)ncols, 0, 1);
+  ensure_krylov_fast(h, L, EL, 1, a);
+  k_derivs_fast<EL, M, NC><<<L.grid, L.threads, L.smem, h->stream>>>(d, a, uv, ncols, cv, adjoint);
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+}
+
+// (EL, NC) shapes built for every M: N <= 32 with 1..3 control operators, N <= 64 with 2..3.
+#define QGD_FAST_SHAPES(X, M) X(1, M, 1) X(1, M, 2) X(1, M, 3) X(2, M, 2) X(2, M, 3)
+
+}  // namespace
+
+#define QGD_FAST_CASE_FWD(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC>(h, d, a); return true; }
+#define QGD_FAST_CASE_BWD(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC>(h, d, a); return true; }
+#define QGD_FAST_CASE_DER(EL, M, NC) if (el == EL && nc == NC) { launch_derivs_fast_t<EL, M, NC>(h, d, a, uv, ncols, cv, adjoint); return true; }
+
+#define QGD_DEFINE_FAST_LAUNCHERS(M)                                                                                        \
+  bool launch_forward_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                              \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_FWD, M) return false;                                                                     \
+  }                                                                                                                         \
+  bool launch_backward_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                             \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_BWD, M) return false;                                                                     \
+  }                                                                                                                         \
+  bool launch_derivs_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc, double* uv, int ncols,          \
+                               const double* cv, int adjoint) {                                                             \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_DER, M) return false;                                                                     \
+  }

@@ -72,6 +72,9 @@ struct qgd_handle {
   int64_t hist_nsteps = 0, hist_save = 0;
   bool hist_valid = false;
   int phase_B = 0, phase_order = 0;  // two-phase API
+  // register-operator fast path (qgd_fast.cuh): structure test done once at creation
+  bool fast_ok = false;
+  int fast_el = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   qgd_stats_t stats{};
 };
@@ -88,3 +91,19 @@ struct qgd_handle {
 QGD_DECLARE_LAUNCHERS(1)
 QGD_DECLARE_LAUNCHERS(2)
 QGD_DECLARE_LAUNCHERS(4)
+
+// Register-operator kernels (qgd_fast.cuh), one translation unit per Taylor depth M = order/2.  Each launcher
+// returns false when the (levels-per-lane, operator count) shape was not built; the caller then uses the
+// generic kernels.
+#define QGD_DECLARE_FAST_LAUNCHERS(M)                                                                              \
+  bool launch_forward_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                     \
+  bool launch_backward_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                    \
+  bool launch_derivs_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc, double* uv, int ncols, \
+                               const double* cv, int adjoint);
+QGD_DECLARE_FAST_LAUNCHERS(1)
+QGD_DECLARE_FAST_LAUNCHERS(2)
+QGD_DECLARE_FAST_LAUNCHERS(3)
+QGD_DECLARE_FAST_LAUNCHERS(4)
+QGD_DECLARE_FAST_LAUNCHERS(5)
+QGD_DECLARE_FAST_LAUNCHERS(6)
+#define QGD_FAST_MAX_M 6

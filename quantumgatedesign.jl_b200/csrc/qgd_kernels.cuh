@@ -21,6 +21,7 @@ struct SweepArgs {
   int B;                 // control vectors in this batch
   int save_every, nslots;
   int warp_smem_doubles; // per-warp shared-memory region
+  int ks;                // fast path: Krylov basis vectors resident in shared memory per warp
   const double* cvals;   // [B][nsteps+1][2][m+1][Nc]
   double* history;       // [2N][1+m][nslots][ncol][B]
   double* final_state;   // [2N][ncol][B]

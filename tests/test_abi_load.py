@@ -33,7 +33,7 @@ def test_struct_layout_matches_header(q):
     assert ctypes.sizeof(A.qgd_matrix_t) == 64
     assert ctypes.sizeof(A.qgd_control_t) == 64
     assert ctypes.sizeof(A.qgd_problem_t) == 32 + 2 * 64 + 4 * 8 + 64 + 8 + 8 + 16 + 8 + 8
-    assert ctypes.sizeof(A.qgd_stats_t) == 48
+    assert ctypes.sizeof(A.qgd_stats_t) == 56
 
 
 def test_n_coeff_helpers(q):

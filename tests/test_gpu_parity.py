@@ -114,6 +114,18 @@ def test_gradient_parity(q, O, name):
     h.close()
 
 
+@pytest.mark.parametrize("name,expect_fast", [("cnot2", True), ("cnot3_333", True), ("cnot3_444_short", True),
+                                              ("rabi_carrier", True), ("dense_o10", False), ("rand_grape", False)])
+def test_kernel_selection(q, name, expect_fast):
+    """Sparse dispersive-style problems run on the register-operator kernels (qgd_fast.cuh), dense ones on the
+    generic ELL kernels; both are covered by the parity tests above."""
+    prob, controls, pcof, target, order = _cases(q)[name]
+    h = q.Handle(prob, controls)
+    h.discrete_adjoint(pcof, q.complex_to_real(target), order=order)
+    assert (h.stats()["fast_path_launches"] == 2) == expect_fast
+    h.close()
+
+
 @pytest.mark.parametrize("precond", ["identity", "lu", "diagonal"])
 def test_preconditioners(q, O, precond):
     prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
