@@ -109,14 +109,16 @@ __device__ __forceinline__ void load_regops(RegOps<EL, NC>& R, const QgdDevProb&
 // ---- per-warp context ----------------------------------------------------------------------------------
 template <int EL>
 struct FastCtx {
-  int lane, N, N2, KS;
+  int lane, N, N2;
+  int KT, KS;     // Krylov vectors [0,KT) live in TMEM, [KT,KT+KS) in shared memory, the rest in L2
+  uint32_t tm;    // TMEM address of this warp's region (its 32 lanes, its column range)
   double2* xs;    // smem [2][32*EL]   (u,v) gather buffers (double buffered)
   double2* cv;    // smem [M+1][NC]    (p_k^(d)/d!, q_k^(d)/d!) of the current time level
   double* nullv;  // smem [N2+2]       left null vector of the residual recurrence
-  double2* rot;   // smem [N2+2]       Givens (cs, sn)
+  double2* rot;   // smem [N2+2]       rot[0] = (1,0); rot[i+1] = Givens (cs, sn) of rotation i
   double* g;      // smem [N2+2]       rotated right-hand side, then the least-squares solution
-  double2* Vs;    // smem [KS][32*EL]  Krylov basis, resident part
-  double2* Vg;    // global            Krylov basis, tail (vector i >= KS at (i-KS)*32*EL)
+  double2* Vs;    // smem [KS][32*EL]  Krylov basis, shared-memory tier
+  double2* Vg;    // global            Krylov basis, tail (vector i >= KT+KS at (i-KT-KS)*32*EL)
   double* Rg;     // global            packed upper-triangular R: column j at j(j+1)/2
 };
 template <int EL, int M, int NC>
@@ -304,37 +306,132 @@ __device__ __forceinline__ void precond_fast(const RegOps<EL, NC>& R, Vec<EL>& x
   }
 }
 
-// ---- Krylov basis access: resident part in shared memory, tail in L2 ---------------------------------
+// ---- Tensor memory as a scratchpad ---------------------------------------------------------------------
+// The FP64 path never touches the 5th-generation tensor cores, so their 256 KB of TMEM per SM is idle: each
+// warp parks Krylov vectors in the 32 TMEM lanes it may address (lane quarter = warp % 4) with tcgen05.st and
+// reads them back with tcgen05.ld (32x32b shape: lane l <-> TMEM lane, 4*EL consecutive 32-bit columns = its
+// 2*EL doubles of one vector).  Measured on B200 (tools/tmem_test.cu): 23 cycles load-to-use, > 380 B/clk/SM.
+__device__ __forceinline__ uint32_t tmem_alloc_cols(uint32_t* slot_smem, uint32_t ncols) {  // whole CTA calls; returns the base address
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *slot_smem;
+}
+__device__ __forceinline__ void tmem_free_cols(uint32_t base, uint32_t ncols) {  // whole CTA calls
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void u2(double v, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)__double2loint(v); hi = (uint32_t)__double2hiint(v); }
+__device__ __forceinline__ double d2(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+
+template <int EL>
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const Vec<EL>& a) {
+  static_assert(EL == 1 || EL == 2, "TMEM tier is built for EL <= 2");
+  uint32_t r[4 * EL];
+#pragma unroll
+  for (int e = 0; e < EL; ++e) { u2(a.u[e], r[4 * e], r[4 * e + 1]); u2(a.v[e], r[4 * e + 2], r[4 * e + 3]); }
+  if constexpr (EL == 2)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+  else
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// issue only; the registers are valid after tmem_wait_ld()
+template <int EL>
+__device__ __forceinline__ void tmem_load_issue(uint32_t taddr, uint32_t (&r)[4 * EL]) {
+  if constexpr (EL == 2)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+  else
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int EL>
+__device__ __forceinline__ void tmem_unpack(const uint32_t (&r)[4 * EL], Vec<EL>& a) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) { a.u[e] = d2(r[4 * e], r[4 * e + 1]); a.v[e] = d2(r[4 * e + 2], r[4 * e + 3]); }
+}
+template <int EL>
+__device__ __forceinline__ void tmem_load(uint32_t taddr, Vec<EL>& a) {
+  uint32_t r[4 * EL];
+  tmem_load_issue<EL>(taddr, r);
+  tmem_wait_ld();
+  tmem_unpack<EL>(r, a);
+}
+
+// ---- Krylov basis access: TMEM tier, shared-memory tier, L2 tail ---------------------------------------
 template <int EL>
 __device__ __forceinline__ void basis_load(const FastCtx<EL>& c, int i, Vec<EL>& a) {
-  if (i < c.KS) v2_load<EL>(a, c.Vs + (size_t)i * 32 * EL, c.lane);
-  else v2_load_cg<EL>(a, c.Vg + (size_t)(i - c.KS) * 32 * EL, c.lane);
+  if (i < c.KT) tmem_load<EL>(c.tm + 4 * EL * i, a);
+  else if (i < c.KT + c.KS) v2_load<EL>(a, c.Vs + (size_t)(i - c.KT) * 32 * EL, c.lane);
+  else v2_load_cg<EL>(a, c.Vg + (size_t)(i - c.KT - c.KS) * 32 * EL, c.lane);
 }
 template <int EL>
 __device__ __forceinline__ void basis_store(const FastCtx<EL>& c, int i, const Vec<EL>& a) {
-  if (i < c.KS) v2_store<EL>(c.Vs + (size_t)i * 32 * EL, a, c.lane);
-  else v2_store<EL>(c.Vg + (size_t)(i - c.KS) * 32 * EL, a, c.lane);
+  if (i < c.KT) tmem_store<EL>(c.tm + 4 * EL * i, a);
+  else if (i < c.KT + c.KS) v2_store<EL>(c.Vs + (size_t)(i - c.KT) * 32 * EL, a, c.lane);
+  else v2_store<EL>(c.Vg + (size_t)(i - c.KT - c.KS) * 32 * EL, a, c.lane);
 }
 
 __device__ __forceinline__ int roff(int j) { return (j * (j + 1)) >> 1; }
 
-// Solve R y = g (R upper triangular, packed columns in global memory), y overwrites c.g (shared).
+// Solve R y = g (R upper triangular, packed columns in L2), y overwrites c.g (shared).  Column j-1 is
+// fetched while column j is being eliminated.
 template <int EL>
 __device__ __forceinline__ void trsv_fast(const FastCtx<EL>& c, int width) {
   const int lane = c.lane;
+  constexpr int CH = 4;  // rows handled per lane: width <= restart <= 128
+  double cur[CH], nxt[CH], dcur, dnxt = 0.0;
+  {
+    const double* col = c.Rg + roff(width - 1);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; cur[q] = i < width - 1 ? __ldcg(col + i) : 0.0; }
+    dcur = __ldcg(col + width - 1);
+  }
   __syncwarp();
   for (int j = width - 1; j >= 0; --j) {
-    const double* col = c.Rg + roff(j);
-    const double yj = c.g[j] / __ldcg(col + j);
+    if (j > 0) {
+      const double* col = c.Rg + roff(j - 1);
+#pragma unroll
+      for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; nxt[q] = i < j - 1 ? __ldcg(col + i) : 0.0; }
+      dnxt = __ldcg(col + j - 1);
+    }
+    const double yj = c.g[j] / dcur;
     __syncwarp();
-    if (lane == 0) c.g[j] = yj;
-    for (int i = lane; i < j; i += 32) c.g[i] = fma(-yj, __ldcg(col + i), c.g[i]);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const int i = lane + 32 * q;
+      if (i < j) c.g[i] = fma(-yj, cur[q], c.g[i]);
+      else if (i == j) c.g[i] = yj;
+    }
     __syncwarp();
+#pragma unroll
+    for (int q = 0; q < CH; ++q) cur[q] = nxt[q];
+    dcur = dnxt;
   }
 }
 
+// One modified Gram-Schmidt step against basis vector i (already in registers) fused with the progressive
+// Givens update of the Hessenberg column: branch free; nul = nullv[i], rt = rot[i] (rot[0] = identity).
+template <int EL>
+__device__ __forceinline__ void mgs_step(int i, const Vec<EL>& vi, Vec<EL>& w, double& dsum, double& hprev, double* rcol, double nul,
+                                         double2 rt) {
+  const double h = warp_allsum(vdot_local<EL>(vi, w));
+  vaxpy(w, -h, vi);
+  dsum = fma(nul, h, dsum);
+  const double r = rt.x * hprev + rt.y * h;  // row i-1 of R, final after rotation i-1
+  hprev = -rt.y * hprev + rt.x * h;
+  if (i > 0) rcol[i - 1] = r;                 // every lane, same address, same value
+}
+
 // GMRES for the time-stepping solves (fixed absolute tolerance, restart = maxiter = 2N).
-// OP: apply(in, out) = A in; left preconditioner applied here.  Returns the number of iterations.
+// OP: apply(in, out) = A in; the left preconditioner is applied here.  Returns the number of iterations.
 template <int EL, int NC, class OP>
 __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
                           int restart, int maxiter) {
@@ -349,32 +446,61 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
   basis_store<EL>(c, 0, v);
   double cur = beta, res_beta = beta, accum = 1.0, gcur = beta;
   __syncwarp();
-  if (lane == 0) c.nullv[0] = 1.0;
+  if (lane == 0) { c.nullv[0] = 1.0; c.rot[0] = make_double2(1.0, 0.0); }
   __syncwarp();
   int k = 1, it = 0;
   while (it < maxiter && cur > tol) {
     op.apply(v, w);  // expand!
     precond_fast<EL, NC>(R, w);
-    // modified Gram-Schmidt against V[:, 0..k-1]; rotation i-1 is applied to (h_{i-1}, h_i) as soon as h_i exists
+    // modified Gram-Schmidt against V[:, 0..k-1], tier by tier; the next vector and its scalars are fetched while
+    // the current one is being reduced
     double dsum = 0.0, hprev = 0.0;
     double* rcol = c.Rg + roff(k - 1);
-    Vec<EL> vi;
-    basis_load<EL>(c, 0, vi);
-    for (int i = 0; i < k; ++i) {
-      Vec<EL> vn;
-      if (i + 1 < k) basis_load<EL>(c, i + 1, vn);
-      const double h = warp_allsum(vdot_local<EL>(vi, w));
-      vaxpy(w, -h, vi);
-      dsum = fma(c.nullv[i], h, dsum);
-      if (i > 0) {
-        const double2 cs = c.rot[i - 1];
-        const double r = cs.x * hprev + cs.y * h;
-        hprev = -cs.y * hprev + cs.x * h;
-        if (lane == 0) rcol[i - 1] = r;
-      } else {
-        hprev = h;
+    const int nT = min(k, c.KT), nS = min(k, c.KT + c.KS);
+    int i = 0;
+    if (nT > 0) {  // ---- TMEM tier
+      uint32_t rn[4 * EL];
+      Vec<EL> vi;
+      tmem_load<EL>(c.tm, vi);
+      double nul = c.nullv[0];
+      double2 rt = c.rot[0];
+      for (; i < nT; ++i) {
+        const bool more = i + 1 < nT;
+        double nul_n = 0.0;
+        double2 rt_n = make_double2(0.0, 0.0);
+        if (more) { tmem_load_issue<EL>(c.tm + 4 * EL * (i + 1), rn); nul_n = c.nullv[i + 1]; rt_n = c.rot[i + 1]; }
+        mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
+        if (more) { tmem_wait_ld(); tmem_unpack<EL>(rn, vi); nul = nul_n; rt = rt_n; }
       }
-      if (i + 1 < k) vi = vn;
+    }
+    if (i < nS) {  // ---- shared-memory tier
+      Vec<EL> vi, vn;
+      v2_load<EL>(vi, c.Vs + (size_t)(i - c.KT) * 32 * EL, lane);
+      double nul = c.nullv[i];
+      double2 rt = c.rot[i];
+      for (; i < nS; ++i) {
+        const bool more = i + 1 < nS;
+        double nul_n = 0.0;
+        double2 rt_n = make_double2(0.0, 0.0);
+        if (more) { v2_load<EL>(vn, c.Vs + (size_t)(i + 1 - c.KT) * 32 * EL, lane); nul_n = c.nullv[i + 1]; rt_n = c.rot[i + 1]; }
+        mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
+        if (more) { vi = vn; nul = nul_n; rt = rt_n; }
+      }
+    }
+    if (i < k) {  // ---- L2 tail
+      Vec<EL> vi, vn;
+      const double2* base = c.Vg - (size_t)(c.KT + c.KS) * 32 * EL;
+      v2_load_cg<EL>(vi, base + (size_t)i * 32 * EL, lane);
+      double nul = c.nullv[i];
+      double2 rt = c.rot[i];
+      for (; i < k; ++i) {
+        const bool more = i + 1 < k;
+        double nul_n = 0.0;
+        double2 rt_n = make_double2(0.0, 0.0);
+        if (more) { v2_load_cg<EL>(vn, base + (size_t)(i + 1) * 32 * EL, lane); nul_n = c.nullv[i + 1]; rt_n = c.rot[i + 1]; }
+        mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
+        if (more) { vi = vn; nul = nul_n; rt = rt_n; }
+      }
     }
     const double nrm = sqrt(warp_allsum(vdot_local<EL>(w, w)));
     vscale(w, 1.0 / nrm);
@@ -382,9 +508,9 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
     {  // new rotation (k-1) from (hprev, nrm); update the rotated right-hand side
       double cs, sn;
       givens(hprev, nrm, cs, sn);
+      rcol[k - 1] = cs * hprev + sn * nrm;
       if (lane == 0) {
-        rcol[k - 1] = cs * hprev + sn * nrm;
-        c.rot[k - 1] = make_double2(cs, sn);
+        c.rot[k] = make_double2(cs, sn);
         c.g[k - 1] = cs * gcur;
       }
       gcur = -sn * gcur;
@@ -399,6 +525,7 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
     if (k == restart + 1 || cur <= tol) {
       const int width = k - 1;
       trsv_fast<EL>(c, width);
+      Vec<EL> vi;
       basis_load<EL>(c, 0, vi);
       for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 0..width-1] y
         Vec<EL> vn;
@@ -450,14 +577,21 @@ __device__ __forceinline__ void load_cv_fast(const FastCtx<EL>& c, const double*
   __syncwarp();
 }
 
-// shared-memory carve-up: [warp regions]; each region = fixed part + KS basis vectors (+ extra doubles)
+// shared-memory carve-up: [16 bytes: TMEM address slot][warp regions]; each region = fixed part + KS basis
+// vectors (+ extra doubles)
 template <int EL, int M, int NC>
-__device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra) {
+__device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra,
+                                                     uint32_t tmem_base) {
   FastCtx<EL> c;
   c.lane = threadIdx.x & 31;
   c.N = d.N; c.N2 = d.N2; c.KS = a.ks;
   const int warp = threadIdx.x >> 5;
-  double* w = reinterpret_cast<double*>(smem) + (size_t)warp * a.warp_smem_doubles;
+  // TMEM: warp w may address lanes [32 (w % 4), +32); warps w and w + 4 split the 512 columns
+  const int groups = ((blockDim.x >> 5) + 3) >> 2;
+  const int cols = a.tmem_cols / groups;
+  c.KT = a.kt;
+  c.tm = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cols * (warp >> 2));
+  double* w = reinterpret_cast<double*>(smem + 16) + (size_t)warp * a.warp_smem_doubles;
   c.xs = reinterpret_cast<double2*>(w); w += 2 * 2 * 32 * EL;
   c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
   c.rot = reinterpret_cast<double2*>(w); w += 2 * (d.N2 + 2);
@@ -476,7 +610,8 @@ template <int EL, int M, int NC>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra);
+  const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra, tmem_base);
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2;
   RegOps<EL, NC> R;
@@ -516,6 +651,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
       vstore(x, a.final_state + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b), N, lane);
     }
   }
+  if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 // grad_acc[theta] -= sum_r table_p[r][theta] gK[r][k(theta)] + table_q[r][theta] gS[r][k(theta)]
@@ -543,7 +679,8 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
                                                                                const QgdDevControl* __restrict__ ctrls) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra);
+  const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra, tmem_base);
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2, Nt = d.nsteps + 1, P = d.P;
   RegOps<EL, NC> R;
@@ -624,6 +761,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
     for (int t = lane; t < P; t += 32) a.gradcol[(size_t)t + (size_t)P * ((size_t)cl + (size_t)d.ncol * b)] = gacc[t];
     __syncwarp();
   }
+  if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 // K2 on its own (tests): uv [2N][1+m][ncols]; forward Taylor columns or Lambda_j = W_j^T x.
@@ -632,7 +770,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_derivs_fast(const
                                                                              int ncols, const double* cv, int adjoint) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra);
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra, 0u);
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2;
   RegOps<EL, NC> R;

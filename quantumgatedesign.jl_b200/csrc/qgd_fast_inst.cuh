@@ -3,12 +3,14 @@
 // kernels compile in parallel translation units.
 #pragma once
 #include "qgd_host.h"
+#include <cstdlib>
+
 #include "qgd_fast.cuh"
 
 namespace {
 using namespace qgd;
 
-struct FastCfg { int grid, threads, wpc, ks, warp_doubles; size_t smem; };
+struct FastCfg { int grid, threads, wpc, ks, kt, tmem_cols, warp_doubles; size_t smem; };
 
 // One CTA per SM, all of its shared memory split between the warps; whatever is left after the fixed
 // per-warp arrays holds the resident part of the Krylov basis.
@@ -20,14 +22,25 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   L.wpc = (int)std::min<size_t>(QGD_WARPS_PER_CTA, std::max<size_t>(1, (items + sms - 1) / sms));
   const int vec = 2 * 32 * el;
   const int base = (fixed_doubles + extra_doubles + 1) & ~1;
-  const long per_warp = (long)(max_smem / 8 / L.wpc) & ~1L;
+  // tensor-memory tier: warps w and w + 4 of a CTA share a lane quarter, so each gets 512 / groups columns;
+  // a vector takes 4 * el columns.  Allocation must be a power of two >= 32 columns.
+  const int groups = (L.wpc + 3) / 4;
+  L.kt = restart >= 2 && getenv("QGD_DISABLE_TMEM") == nullptr ? std::min(restart + 1, (512 / groups) / (4 * el)) : 0;
+  L.tmem_cols = 0;
+  if (L.kt > 0) {
+    int need = groups * L.kt * 4 * el, pow2 = 32;
+    while (pow2 < need) pow2 *= 2;
+    L.tmem_cols = pow2;
+    L.kt = std::min(restart + 1, (pow2 / groups) / (4 * el));
+  }
+  const long per_warp = (long)((max_smem - 16) / 8 / L.wpc) & ~1L;
   long ks = (per_warp - base) / vec;
-  ks = std::min<long>(ks, restart + 1);
-  if (ks < 2) throw QgdError(QGD_EUNSUPPORTED, "fast path: shared memory too small for the per-warp state");
+  ks = std::min<long>(ks, std::max(restart + 1 - L.kt, 0));
+  if (ks < 0) throw QgdError(QGD_EUNSUPPORTED, "fast path: shared memory too small for the per-warp state");
   L.ks = (int)ks;
   L.warp_doubles = base + (int)ks * vec;
   L.threads = 32 * L.wpc;
-  L.smem = (size_t)L.wpc * L.warp_doubles * 8;
+  L.smem = 16 + (size_t)L.wpc * L.warp_doubles * 8;
   CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
   const size_t ctas = (items + L.wpc - 1) / L.wpc;
   L.grid = (int)std::max<size_t>(1, std::min<size_t>(ctas, (size_t)sms));
@@ -36,13 +49,13 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
 
 void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, SweepArgs& a) {
   const size_t warps = (size_t)L.grid * L.wpc;
-  a.v_stride = (size_t)std::max(restart + 1 - L.ks, 1) * 2 * 32 * el;
+  a.v_stride = (size_t)std::max(restart + 1 - L.ks - L.kt, 1) * 2 * 32 * el;
   a.h_stride = (size_t)restart * (restart + 3) / 2 + 2;
   h->d_V.reserve(warps * a.v_stride * 8);
   h->d_H.reserve(warps * a.h_stride * 8);
   a.Vws = h->d_V.as<double>();
   a.Hws = h->d_H.as<double>();
-  a.ks = L.ks;
+  a.ks = L.ks; a.kt = L.kt; a.tmem_cols = L.tmem_cols;
   a.warp_smem_doubles = L.warp_doubles;
 }
 
