@@ -27,9 +27,9 @@ namespace qgd {
 #endif
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
-               : "=d"(d0), "=d"(d1)
-               : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+      : "=d"(d0), "=d"(d1)
+      : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
 }
 
 // Sum of one double per lane, result in every lane.
@@ -62,7 +62,7 @@ struct RegOps {
   int col[EL][NC][2];       // gather column of entry s of row (lane + 32 e) of control operator k
   double vk[EL][NC][2];     // K_c value
   double vs[EL][NC][2];     // S_c value
-  double pr_ratio[EL], pr_up[EL], pr_den[EL], pr_dg[EL];  // DiagonalHamiltonianPreconditioner
+  double pr_ratio[EL], pr_up[EL], pr_rden[EL], pr_rdg[EL];  // DiagonalHamiltonianPreconditioner (reciprocal pivots)
   double wu[EL], wv[EL];    // guard projector diagonal (u rows, v rows)
 };
 
@@ -90,12 +90,12 @@ __device__ __forceinline__ void load_regops(RegOps<EL, NC>& R, const QgdDevProb&
     }
     if (d.precond == QGD_PRECOND_DIAGONAL && dir >= 0) {
       const double* pd = reinterpret_cast<const double*>(d.blob + L.off_pre[dir]);
-      R.pr_dg[e] = ok ? pd[r] : 1.0;
+      R.pr_rdg[e] = ok ? 1.0 / pd[r] : 1.0;
       R.pr_up[e] = ok ? pd[d.N2 + r] : 0.0;
       R.pr_ratio[e] = ok ? pd[d.N2 + N + r] : 0.0;
-      R.pr_den[e] = ok ? pd[d.N2 + 2 * N + r] : 1.0;
+      R.pr_rden[e] = ok ? 1.0 / pd[d.N2 + 2 * N + r] : 1.0;
     } else {
-      R.pr_dg[e] = 1.0; R.pr_up[e] = 0.0; R.pr_ratio[e] = 0.0; R.pr_den[e] = 1.0;
+      R.pr_rdg[e] = 1.0; R.pr_up[e] = 0.0; R.pr_ratio[e] = 0.0; R.pr_rden[e] = 1.0;
     }
     if (L.LW > 0 && ok) {
       const double* wv = reinterpret_cast<const double*>(d.blob + L.off_wval);
@@ -296,12 +296,11 @@ __device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, 
 
 template <int EL, int NC>
 __device__ __forceinline__ void precond_fast(const RegOps<EL, NC>& R, Vec<EL>& x) {  // preconditioners.jl:108-126
+  // the two pivot divisions of the reference are multiplications by reciprocals formed once per sweep (<= 1 ulp apart)
 #pragma unroll
   for (int e = 0; e < EL; ++e) {
-    double xv = x.v[e] - x.u[e] * R.pr_ratio[e];
-    xv = xv / R.pr_den[e];
-    double xu = x.u[e] - R.pr_up[e] * xv;
-    xu = xu / R.pr_dg[e];
+    const double xv = (x.v[e] - x.u[e] * R.pr_ratio[e]) * R.pr_rden[e];
+    const double xu = (x.u[e] - R.pr_up[e] * xv) * R.pr_rdg[e];
     x.u[e] = xu; x.v[e] = xv;
   }
 }
@@ -381,8 +380,19 @@ __device__ __forceinline__ void basis_store(const FastCtx<EL>& c, int i, const V
 
 __device__ __forceinline__ int roff(int j) { return (j * (j + 1)) >> 1; }
 
-// Solve R y = g (R upper triangular, packed columns in L2), y overwrites c.g (shared).  Column j-1 is
-// fetched while column j is being eliminated.
+// LinearAlgebra.givensAlgorithm for reals with one reciprocal square root instead of sqrt + two divisions
+__device__ __forceinline__ void givens_fast(double f, double g, double& cs, double& sn) {
+  if (g == 0.0) { cs = 1.0; sn = 0.0; }
+  else if (f == 0.0) { cs = 0.0; sn = 1.0; }
+  else {
+    const double rr = rsqrt(fma(f, f, g * g));
+    cs = f * rr; sn = g * rr;
+    if (fabs(f) > fabs(g) && cs < 0.0) { cs = -cs; sn = -sn; }
+  }
+}
+
+// Solve R y = g (R upper triangular, packed columns in L2 with RECIPROCAL diagonal), y overwrites c.g (shared).
+// Column j-1 is fetched while column j is being eliminated.
 template <int EL>
 __device__ __forceinline__ void trsv_fast(const FastCtx<EL>& c, int width) {
   const int lane = c.lane;
@@ -402,7 +412,7 @@ __device__ __forceinline__ void trsv_fast(const FastCtx<EL>& c, int width) {
       for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; nxt[q] = i < j - 1 ? __ldcg(col + i) : 0.0; }
       dnxt = __ldcg(col + j - 1);
     }
-    const double yj = c.g[j] / dcur;
+    const double yj = c.g[j] * dcur;  // dcur = 1 / R[j][j]
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < CH; ++q) {
@@ -441,8 +451,9 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
 #pragma unroll
   for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
   precond_fast<EL, NC>(R, v);
-  double beta = sqrt(warp_allsum(vdot_local<EL>(v, v)));
-  vscale(v, 1.0 / beta);
+  double beta2 = warp_allsum(vdot_local<EL>(v, v));
+  double rbeta = rsqrt(beta2), beta = beta2 * rbeta;
+  vscale(v, rbeta);
   basis_store<EL>(c, 0, v);
   double cur = beta, res_beta = beta, accum = 1.0, gcur = beta;
   __syncwarp();
@@ -465,12 +476,14 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
       double nul = c.nullv[0];
       double2 rt = c.rot[0];
       for (; i < nT; ++i) {
-        const bool more = i + 1 < nT;
-        double nul_n = 0.0;
-        double2 rt_n = make_double2(0.0, 0.0);
-        if (more) { tmem_load_issue<EL>(c.tm + 4 * EL * (i + 1), rn); nul_n = c.nullv[i + 1]; rt_n = c.rot[i + 1]; }
+        const int inext = min(i + 1, c.KT - 1);  // always a valid slot: no predicate in the loop body
+        tmem_load_issue<EL>(c.tm + 4 * EL * inext, rn);
+        const double nul_n = c.nullv[i + 1];
+        const double2 rt_n = c.rot[i + 1];
         mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
-        if (more) { tmem_wait_ld(); tmem_unpack<EL>(rn, vi); nul = nul_n; rt = rt_n; }
+        tmem_wait_ld();
+        tmem_unpack<EL>(rn, vi);
+        nul = nul_n; rt = rt_n;
       }
     }
     if (i < nS) {  // ---- shared-memory tier
@@ -479,46 +492,48 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
       double nul = c.nullv[i];
       double2 rt = c.rot[i];
       for (; i < nS; ++i) {
-        const bool more = i + 1 < nS;
-        double nul_n = 0.0;
-        double2 rt_n = make_double2(0.0, 0.0);
-        if (more) { v2_load<EL>(vn, c.Vs + (size_t)(i + 1 - c.KT) * 32 * EL, lane); nul_n = c.nullv[i + 1]; rt_n = c.rot[i + 1]; }
+        const int inext = min(i + 1 - c.KT, c.KS - 1);
+        v2_load<EL>(vn, c.Vs + (size_t)inext * 32 * EL, lane);
+        const double nul_n = c.nullv[i + 1];
+        const double2 rt_n = c.rot[i + 1];
         mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
-        if (more) { vi = vn; nul = nul_n; rt = rt_n; }
+        vi = vn; nul = nul_n; rt = rt_n;
       }
     }
-    if (i < k) {  // ---- L2 tail
-      Vec<EL> vi, vn;
+    if (i < k) {  // ---- L2 tail (two vectors in flight)
+      Vec<EL> vi, vn, vnn;
       const double2* base = c.Vg - (size_t)(c.KT + c.KS) * 32 * EL;
       v2_load_cg<EL>(vi, base + (size_t)i * 32 * EL, lane);
+      v2_load_cg<EL>(vn, base + (size_t)min(i + 1, k - 1) * 32 * EL, lane);
       double nul = c.nullv[i];
       double2 rt = c.rot[i];
       for (; i < k; ++i) {
-        const bool more = i + 1 < k;
-        double nul_n = 0.0;
-        double2 rt_n = make_double2(0.0, 0.0);
-        if (more) { v2_load_cg<EL>(vn, base + (size_t)(i + 1) * 32 * EL, lane); nul_n = c.nullv[i + 1]; rt_n = c.rot[i + 1]; }
+        v2_load_cg<EL>(vnn, base + (size_t)min(i + 2, k - 1) * 32 * EL, lane);
+        const double nul_n = c.nullv[i + 1];
+        const double2 rt_n = c.rot[i + 1];
         mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
-        if (more) { vi = vn; nul = nul_n; rt = rt_n; }
+        vi = vn; vn = vnn; nul = nul_n; rt = rt_n;
       }
     }
-    const double nrm = sqrt(warp_allsum(vdot_local<EL>(w, w)));
-    vscale(w, 1.0 / nrm);
+    const double nrm2 = warp_allsum(vdot_local<EL>(w, w));
+    const double rnrm = rsqrt(nrm2), nrm = nrm2 * rnrm;  // 1/||w|| and ||w|| from one reciprocal square root
+    vscale(w, rnrm);
     basis_store<EL>(c, k, w);
     {  // new rotation (k-1) from (hprev, nrm); update the rotated right-hand side
       double cs, sn;
-      givens(hprev, nrm, cs, sn);
-      rcol[k - 1] = cs * hprev + sn * nrm;
+      givens_fast(hprev, nrm, cs, sn);
+      const double rkk = cs * hprev + sn * nrm;
+      rcol[k - 1] = 1.0 / rkk;  // the triangular solve only ever divides by the diagonal: keep its reciprocal
       if (lane == 0) {
         c.rot[k] = make_double2(cs, sn);
         c.g[k - 1] = cs * gcur;
       }
       gcur = -sn * gcur;
     }
-    const double nv = -(dsum / nrm);  // update_residual!
+    const double nv = -(dsum * rnrm);  // update_residual!
     if (lane == 0) c.nullv[k] = nv;
     accum = fma(nv, nv, accum);
-    cur = res_beta / sqrt(accum);
+    cur = res_beta * rsqrt(accum);
     k += 1;
     v = w;
     __syncwarp();
@@ -539,8 +554,9 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
 #pragma unroll
         for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
         precond_fast<EL, NC>(R, v);
-        beta = sqrt(warp_allsum(vdot_local<EL>(v, v)));
-        vscale(v, 1.0 / beta);
+        beta2 = warp_allsum(vdot_local<EL>(v, v));
+        rbeta = rsqrt(beta2); beta = beta2 * rbeta;
+        vscale(v, rbeta);
         basis_store<EL>(c, 0, v);
         accum = 1.0; res_beta = beta; gcur = beta;
         __syncwarp();
@@ -568,6 +584,12 @@ struct AdjOpFast {  // LHSHolderAdjoint (:624-633) through the reverse sweep
     adj_fast<EL, M, NC, false>(c, R, in, a_lhs, out, nullptr, dK, dS);
   }
 };
+
+__device__ __forceinline__ size_t next_item(unsigned int* counter, int lane) {
+  unsigned int v = 0;
+  if (lane == 0) v = atomicAdd(counter, 1u);
+  return (size_t)__shfl_sync(FULL_MASK, v, 0);
+}
 
 // control Taylor coefficients of a time level: global [2][M+1][NC] -> shared (p, q) pairs [M+1][NC]
 template <int EL, int M, int NC>
@@ -623,7 +645,8 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
   const size_t cv_stride = (size_t)2 * (M + 1) * NC;
   const size_t slot_sz = (size_t)N2 * (M + 1);
   const FwdOpFast<EL, M, NC> op{c, R, a_lhs};
-  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+  // columns need different numbers of GMRES iterations: warps draw (control vector, column) items from a queue
+  for (size_t item = next_item(a.work_counter, lane); item < items; item = next_item(a.work_counter, lane)) {
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
     const double* cvb = a.cvals + (size_t)b * (d.nsteps + 1) * cv_stride;
     double* hist = a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b);
@@ -697,7 +720,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
   double* gSs = gKs + M * NC;    // [M][NC] reduced g^S
   const AdjOpFast<EL, M, NC> op{c, R, a_lhs};
   const double fsc = -2.0 * d.dt / d.tf;
-  for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
+  for (size_t item = next_item(a.work_counter, lane); item < items; item = next_item(a.work_counter, lane)) {
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
     const double* cvb = a.cvals + (size_t)b * Nt * cv_stride;
     const double* hist = a.history + slot_sz * Nt * ((size_t)cl + (size_t)d.ncol * b);

@@ -55,6 +55,9 @@ void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, Sw
   h->d_H.reserve(warps * a.h_stride * 8);
   a.Vws = h->d_V.as<double>();
   a.Hws = h->d_H.as<double>();
+  h->d_counter.reserve(64);
+  CUDA_CHECK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+  a.work_counter = h->d_counter.as<unsigned int>();
   a.ks = L.ks; a.kt = L.kt; a.tmem_cols = L.tmem_cols;
   a.warp_smem_doubles = L.warp_doubles;
 }

@@ -24,6 +24,7 @@ struct SweepArgs {
   int ks;                // fast path: Krylov basis vectors resident in shared memory per warp
   int kt;                // fast path: Krylov basis vectors resident in tensor memory per warp
   int tmem_cols;         // fast path: TMEM columns the CTA allocates (0: none; power of two >= 32)
+  unsigned int* work_counter;  // fast path: item queue head (zeroed before the launch)
   const double* cvals;   // [B][nsteps+1][2][m+1][Nc]
   double* history;       // [2N][1+m][nslots][ncol][B]
   double* final_state;   // [2N][ncol][B]
