@@ -25,6 +25,15 @@ namespace qgd {
 #ifndef QGD_FAST_RED
 #define QGD_FAST_RED 1  // 0: shuffle butterfly, 1: DMMA ones-matrix all-reduce
 #endif
+// Gram-Schmidt block width B.  1: strict modified Gram-Schmidt, one projection at a time, Givens rotations applied
+// progressively (gmres_fast_strict).  4 or 8: the Krylov basis is swept in blocks of B vectors; the B coefficients of
+// a block are taken from the same vector (classical inside a block, modified across blocks), so their warp
+// reductions fuse into one transposing reduction, and the Givens QR of the Hessenberg matrix is done once per solve
+// (as IterativeSolvers' solve_least_squares! does).  The two orthogonalisations differ by h_i <v_i, v_j> = O(eps kappa)
+// inside a block -- the size of the rounding differences between two dot-product orders.
+#ifndef QGD_MGS_BLOCK
+#define QGD_MGS_BLOCK 8
+#endif
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
@@ -115,7 +124,9 @@ struct FastCtx {
   double2* xs;    // smem [2][32*EL]   (u,v) gather buffers (double buffered)
   double2* cv;    // smem [M+1][NC]    (p_k^(d)/d!, q_k^(d)/d!) of the current time level
   double* nullv;  // smem [N2+2]       left null vector of the residual recurrence
-  double2* rot;   // smem [N2+2]       rot[0] = (1,0); rot[i+1] = Givens (cs, sn) of rotation i
+  double2* rot;   // smem [N2+2+8]     rot[0] = (1,0); rot[i+1] = Givens (cs, sn) of rotation i   (strict path)
+  double* hcol;   // smem [N2+10]      same storage as rot (blocked path): current Hessenberg column
+  double* sub;    // smem [N2+2]       same storage as rot (blocked path): subdiagonal H[j+1][j]
   double* g;      // smem [N2+2]       rotated right-hand side, then the least-squares solution
   double2* Vs;    // smem [KS][32*EL]  Krylov basis, shared-memory tier
   double2* Vg;    // global            Krylov basis, tail (vector i >= KT+KS at (i-KT-KS)*32*EL)
@@ -124,7 +135,7 @@ struct FastCtx {
 template <int EL, int M, int NC>
 __host__ __device__ constexpr int fast_fixed_doubles(int N2) {
   // xs + cv + nullv + rot + g
-  return 2 * 2 * 32 * EL + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2) + (N2 + 2);
+  return 2 * 2 * 32 * EL + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
 }
 
 template <int EL>
@@ -443,8 +454,8 @@ __device__ __forceinline__ void mgs_step(int i, const Vec<EL>& vi, Vec<EL>& w, d
 // GMRES for the time-stepping solves (fixed absolute tolerance, restart = maxiter = 2N).
 // OP: apply(in, out) = A in; the left preconditioner is applied here.  Returns the number of iterations.
 template <int EL, int NC, class OP>
-__device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
-                          int restart, int maxiter) {
+__device__ int gmres_fast_strict(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
+                                 int restart, int maxiter) {
   const int lane = c.lane;
   Vec<EL> v, w;
   op.apply(x, w);
@@ -569,6 +580,291 @@ __device__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const O
   return it;
 }
 
+// ========================================================================================================
+// Blocked orthogonalisation (QGD_MGS_BLOCK = 4 or 8)
+// ========================================================================================================
+
+// Sum over the warp of BLK values per lane at once; every lane receives all BLK totals (also left in slot[0..BLK)).
+// log2(BLK) exchange-and-halve shuffle stages leave one value per lane (value index = lane bits 4..), one DMMA with a
+// ones operand sums the remaining lane bits, lanes 0..3 publish the totals through shared memory.
+// Measured on B200 (tools/microbench.cu): DMMA.8x8x4 costs 4 SM-cycles, a 64-bit SHFL 2, so the per-value cost drops
+// from 8.5 (2 DMMA + DADD each) to about 3 SM-cycles.
+template <int BLK>
+__device__ __forceinline__ void block_allsum(double (&p)[BLK], double* slot, int lane) {
+  static_assert(BLK == 4 || BLK == 8, "block width");
+  const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+  double a[BLK / 2];
+#pragma unroll
+  for (int q = 0; q < BLK / 2; ++q) {
+    const double keep = up16 ? p[q + BLK / 2] : p[q], send = up16 ? p[q] : p[q + BLK / 2];
+    a[q] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
+  }
+  double b[BLK / 4];
+#pragma unroll
+  for (int q = 0; q < BLK / 4; ++q) {
+    const double keep = up8 ? a[q + BLK / 4] : a[q], send = up8 ? a[q] : a[q + BLK / 4];
+    b[q] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
+  }
+  double c0, c1;
+  if constexpr (BLK == 8) {
+    const bool up4 = (lane & 4) != 0;
+    const double keep = up4 ? b[1] : b[0], send = up4 ? b[0] : b[1];
+    const double r = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+    dmma884(c0, c1, 1.0, r);  // lane l: totals of values 2(l%4), 2(l%4)+1
+    if (lane < 4) reinterpret_cast<double2*>(slot)[lane] = make_double2(c0, c1);
+  } else {
+    dmma884(c0, c1, 1.0, b[0]);  // lane l: the two halves of the total of value l%4
+    if (lane < 4) slot[lane] = c0 + c1;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < BLK; q += 2) { const double2 t = reinterpret_cast<const double2*>(slot)[q >> 1]; p[q] = t.x; p[q + 1] = t.y; }
+}
+
+// tcgen05.ld of N consecutive 32-bit columns of this warp's 32 TMEM lanes (issue only)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                 "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                 "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 16 || N == 32 || N == 64, "TMEM block load width");
+  if constexpr (N == 16) tmem_ld16(taddr, r);
+  else if constexpr (N == 32) tmem_ld32(taddr, r);
+  else {
+    uint32_t (&lo)[32] = reinterpret_cast<uint32_t (&)[32]>(r[0]);
+    uint32_t (&hi)[32] = reinterpret_cast<uint32_t (&)[32]>(r[32]);
+    tmem_ld32(taddr, lo);
+    tmem_ld32(taddr + 32, hi);
+  }
+}
+
+// Basis vectors i0 .. i0+BLK-1 of one tier (0: TMEM, 1: shared memory, 2: L2).  Tier boundaries are multiples of
+// BLK (plan_fast), so a block never straddles two tiers; slots past the newest vector hold stale but addressable data.
+template <int EL, int BLK, int TIER>
+__device__ __forceinline__ void gs_load_block(const FastCtx<EL>& c, int i0, Vec<EL> (&vb)[BLK]) {
+  if constexpr (TIER == 0) {
+    uint32_t r[4 * EL * BLK];
+    tmem_ld<4 * EL * BLK>(c.tm + 4 * EL * i0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int q = 0; q < BLK; ++q)
+#pragma unroll
+      for (int e = 0; e < EL; ++e) {
+        vb[q].u[e] = d2(r[4 * EL * q + 4 * e], r[4 * EL * q + 4 * e + 1]);
+        vb[q].v[e] = d2(r[4 * EL * q + 4 * e + 2], r[4 * EL * q + 4 * e + 3]);
+      }
+  } else if constexpr (TIER == 1) {
+    const double2* p = c.Vs + (size_t)(i0 - c.KT) * 32 * EL;
+#pragma unroll
+    for (int q = 0; q < BLK; ++q) v2_load<EL>(vb[q], p + (size_t)q * 32 * EL, c.lane);
+  } else {
+    const double2* p = c.Vg + (size_t)(i0 - c.KT - c.KS) * 32 * EL;
+#pragma unroll
+    for (int q = 0; q < BLK; ++q) v2_load_cg<EL>(vb[q], p + (size_t)q * 32 * EL, c.lane);
+  }
+}
+
+// One block: h_q = <v_{i0+q}, w> for the whole block from the same w, then w -= sum_{q < nb} h_q v_{i0+q}.
+// The coefficients are left in c.hcol[i0 .. i0+BLK).
+template <int EL, int BLK>
+__device__ __forceinline__ void gs_block(const FastCtx<EL>& c, int i0, int nb, const Vec<EL> (&vb)[BLK], Vec<EL>& w) {
+  double h[BLK];
+#pragma unroll
+  for (int q = 0; q < BLK; ++q) h[q] = vdot_local<EL>(vb[q], w);
+  block_allsum<BLK>(h, c.hcol + i0, c.lane);
+#pragma unroll
+  for (int q = 0; q < BLK; ++q)
+    if (q < nb) vaxpy(w, -h[q], vb[q]);
+}
+
+// w is orthogonalised against V[:, 0..k-1]; c.hcol[0..k-1] receives the coefficients.
+template <int EL, int BLK>
+__device__ __forceinline__ void gs_orthogonalize(const FastCtx<EL>& c, int k, Vec<EL>& w) {
+  const int eT = min(k, c.KT), eS = min(k, c.KT + c.KS);
+  int i0 = 0;
+  for (; i0 < eT; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 0>(c, i0, vb); gs_block<EL, BLK>(c, i0, k - i0, vb, w); }
+  for (; i0 < eS; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 1>(c, i0, vb); gs_block<EL, BLK>(c, i0, k - i0, vb, w); }
+  for (; i0 < k; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 2>(c, i0, vb); gs_block<EL, BLK>(c, i0, k - i0, vb, w); }
+}
+
+// Least squares  min || H y - beta e_1 ||  for the (width+1) x width Hessenberg matrix packed in c.Rg (L2), as
+// solve_least_squares! does: Givens QR, lanes own the columns j = lane + 32 s, rotation i is formed by the owner of
+// column i and applied by every lane to its columns j > i; then back substitution.  y is left in c.g (shared).
+template <int EL>
+__device__ __forceinline__ void qr_solve_fast(const FastCtx<EL>& c, int width, double beta) {
+  const int lane = c.lane;
+  constexpr int CH = 4;  // width <= restart <= 128
+  const int nsl = (width + 31) >> 5;
+  double top[CH], nxt[CH];
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < CH; ++s) {
+    const int j = lane + 32 * s;
+    const bool ok = j < width;
+    top[s] = ok ? __ldcg(c.Rg + hoff(j)) : 0.0;
+    nxt[s] = ok ? __ldcg(c.Rg + hoff(j) + 1) : 0.0;
+  }
+  double gcur = beta;
+  for (int i = 0; i < width; ++i) {
+    double pre[CH];
+#pragma unroll
+    for (int s = 0; s < CH; ++s) {
+      const int j = lane + 32 * s;
+      pre[s] = (s < nsl && j < width && j > i) ? __ldcg(c.Rg + hoff(j) + i + 2) : 0.0;
+    }
+    const int so = i >> 5;
+    double a_own = top[0];
+#pragma unroll
+    for (int s = 1; s < CH; ++s) a_own = (so == s) ? top[s] : a_own;
+    const double a = __shfl_sync(FULL_MASK, a_own, i & 31);
+    const double b = c.sub[i];
+    double cs, sn;
+    givens_fast(a, b, cs, sn);
+    const double rii = cs * a + sn * b;
+#pragma unroll
+    for (int s = 0; s < CH; ++s) {
+      if (s < nsl) {
+        const int j = lane + 32 * s;
+        if (j < width && j >= i) {
+          const double lo = nxt[s];
+          const double r = cs * top[s] + sn * lo;
+          top[s] = -sn * top[s] + cs * lo;
+          c.Rg[hoff(j) + i] = (j == i) ? 1.0 / rii : r;  // the back substitution only divides by the diagonal
+        }
+        nxt[s] = pre[s];
+      }
+    }
+    if (lane == 0) c.g[i] = cs * gcur;
+    gcur = -sn * gcur;
+  }
+  __syncwarp();
+  // back substitution R y = g, column j-1 fetched while column j is eliminated
+  double cur[CH], nx[CH], dcur, dnxt = 0.0;
+  {
+    const double* col = c.Rg + hoff(width - 1);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; cur[q] = (q < nsl && i < width - 1) ? __ldcg(col + i) : 0.0; }
+    dcur = __ldcg(col + width - 1);
+  }
+  for (int j = width - 1; j >= 0; --j) {
+    if (j > 0) {
+      const double* col = c.Rg + hoff(j - 1);
+#pragma unroll
+      for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; nx[q] = (q < nsl && i < j - 1) ? __ldcg(col + i) : 0.0; }
+      dnxt = __ldcg(col + j - 1);
+    }
+    const double yj = c.g[j] * dcur;  // dcur = 1 / R[j][j]
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      if (q < nsl) {
+        const int i = lane + 32 * q;
+        if (i < j) c.g[i] = fma(-yj, cur[q], c.g[i]);
+        else if (i == j) c.g[i] = yj;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < CH; ++q) cur[q] = nx[q];
+    dcur = dnxt;
+  }
+}
+
+// GMRES with the blocked orthogonalisation; same interface and iteration semantics as gmres_fast_strict.
+template <int EL, int NC, class OP>
+__device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
+                                  int restart, int maxiter) {
+  constexpr int BLK = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 4;
+  const int lane = c.lane;
+  Vec<EL> v, w;
+  op.apply(x, w);
+#pragma unroll
+  for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
+  precond_fast<EL, NC>(R, v);
+  double beta2 = warp_allsum(vdot_local<EL>(v, v));
+  double rbeta = rsqrt(beta2), beta = beta2 * rbeta;
+  vscale(v, rbeta);
+  basis_store<EL>(c, 0, v);
+  double cur = beta, res_beta = beta, accum = 1.0;
+  __syncwarp();
+  if (lane == 0) c.nullv[0] = 1.0;
+  __syncwarp();
+  int k = 1, it = 0;
+  while (it < maxiter && cur > tol) {
+    op.apply(v, w);  // expand!
+    precond_fast<EL, NC>(R, w);
+    gs_orthogonalize<EL, BLK>(c, k, w);
+    // ||w||^2 and the null-vector recurrence <nullvec[0..k), H[0..k, k-1]> (update_residual!)
+    double dpart = 0.0;
+    for (int i = lane; i < k; i += 32) dpart = fma(c.nullv[i], c.hcol[i], dpart);
+    const double nrm2 = warp_allsum(vdot_local<EL>(w, w));
+    const double dsum = warp_allsum(dpart);
+    const double rnrm = rsqrt(nrm2), nrm = nrm2 * rnrm;
+    vscale(w, rnrm);
+    basis_store<EL>(c, k, w);
+    {  // Hessenberg column k-1 (rows 0..k) to the packed matrix in L2
+      double* hc = c.Rg + hoff(k - 1);
+      for (int i = lane; i < k; i += 32) hc[i] = c.hcol[i];
+      if (lane == 0) { hc[k] = nrm; c.sub[k - 1] = nrm; }
+    }
+    const double nv = -(dsum * rnrm);
+    if (lane == 0) c.nullv[k] = nv;
+    accum = fma(nv, nv, accum);
+    cur = res_beta * rsqrt(accum);
+    k += 1;
+    v = w;
+    __syncwarp();
+    if (k == restart + 1 || cur <= tol) {
+      const int width = k - 1;
+      qr_solve_fast<EL>(c, width, res_beta);
+      Vec<EL> vi;
+      basis_load<EL>(c, 0, vi);
+      for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 0..width-1] y
+        Vec<EL> vn;
+        if (j + 1 < width) basis_load<EL>(c, j + 1, vn);
+        vaxpy(x, c.g[j], vi);
+        if (j + 1 < width) vi = vn;
+      }
+      k = 1;
+      if (cur > tol) {  // restart (residual.current keeps its value, as in the package)
+        op.apply(x, w);
+#pragma unroll
+        for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
+        precond_fast<EL, NC>(R, v);
+        beta2 = warp_allsum(vdot_local<EL>(v, v));
+        rbeta = rsqrt(beta2); beta = beta2 * rbeta;
+        vscale(v, rbeta);
+        basis_store<EL>(c, 0, v);
+        accum = 1.0; res_beta = beta;
+        __syncwarp();
+        if (lane == 0) c.nullv[0] = 1.0;
+      }
+      __syncwarp();
+    }
+    it += 1;
+  }
+  return it;
+}
+
+template <int EL, int NC, class OP>
+__device__ __forceinline__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b,
+                                          double tol, int restart, int maxiter) {
+  if constexpr (QGD_MGS_BLOCK > 1) return gmres_fast_blocked<EL, NC, OP>(c, R, op, x, b, tol, restart, maxiter);
+  else return gmres_fast_strict<EL, NC, OP>(c, R, op, x, b, tol, restart, maxiter);
+}
+
 template <int EL, int M, int NC>
 struct FwdOpFast {  // LHSHolder (src/forward_evolution.jl:583-592)
   const FastCtx<EL>& c; const RegOps<EL, NC>& R; const double* a_lhs;
@@ -616,7 +912,7 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   double* w = reinterpret_cast<double*>(smem + 16) + (size_t)warp * a.warp_smem_doubles;
   c.xs = reinterpret_cast<double2*>(w); w += 2 * 2 * 32 * EL;
   c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
-  c.rot = reinterpret_cast<double2*>(w); w += 2 * (d.N2 + 2);
+  c.rot = reinterpret_cast<double2*>(w); c.hcol = w; c.sub = w + d.N2 + 10; w += 2 * (d.N2 + 2 + 8);
   c.nullv = w; w += d.N2 + 2;
   c.g = w; w += d.N2 + 2;
   c.Vs = reinterpret_cast<double2*>(w); w += (size_t)a.ks * 2 * 32 * EL;

@@ -33,11 +33,14 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
     L.tmem_cols = pow2;
     L.kt = std::min(restart + 1, (pow2 / groups) / (4 * el));
   }
+  constexpr int blk = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 1;  // a Gram-Schmidt block never straddles two tiers
+  L.kt = (L.kt / blk) * blk;
   const long per_warp = (long)((max_smem - 16) / 8 / L.wpc) & ~1L;
   long ks = (per_warp - base) / vec;
   ks = std::min<long>(ks, std::max(restart + 1 - L.kt, 0));
   if (ks < 0) throw QgdError(QGD_EUNSUPPORTED, "fast path: shared memory too small for the per-warp state");
-  L.ks = (int)ks;
+  L.ks = (int)(ks / blk) * blk;
+  ks = L.ks;
   L.warp_doubles = base + (int)ks * vec;
   L.threads = 32 * L.wpc;
   L.smem = 16 + (size_t)L.wpc * L.warp_doubles * 8;
@@ -49,7 +52,7 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
 
 void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, SweepArgs& a) {
   const size_t warps = (size_t)L.grid * L.wpc;
-  a.v_stride = (size_t)std::max(restart + 1 - L.ks - L.kt, 1) * 2 * 32 * el;
+  a.v_stride = (size_t)(std::max(restart + 1 - L.ks - L.kt, 1) + QGD_MGS_BLOCK) * 2 * 32 * el;
   a.h_stride = (size_t)restart * (restart + 3) / 2 + 2;
   h->d_V.reserve(warps * a.v_stride * 8);
   h->d_H.reserve(warps * a.h_stride * 8);

@@ -85,6 +85,13 @@ int main() {
     float ms; cudaEventElapsedTime(&ms, e0, e1); double ops = 8.0 * iters * (double)blocks * thr / 32; \
     printf("throughput %-18s %8.3f warp-instr/ns chip  = %6.3f warp-instr/clk/SM (at %.3f GHz nominal)\n", tn[M], ops / (ms * 1e6), ops / (ms * 1e6) / p.multiProcessorCount / ghz, ghz); }
   TP(0) TP(1) TP(2) TP(3)
+  // DFMA issue rate as a function of warps per SM sub-partition (8 independent chains per thread)
+  for (int wps = 1; wps <= 8; wps *= 2) {
+    const int blocks = p.multiProcessorCount, thr = 128 * wps, iters = 16384;
+    k_tput<0><<<blocks, thr>>>(d, iters); cudaEventRecord(e0); k_tput<0><<<blocks, thr>>>(d, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); double ops = 8.0 * iters * (double)blocks * thr / 32;
+    printf("DFMA, %d warp(s) per sub-partition: %6.3f warp-instr/clk/SM\n", wps, ops / (ms * 1e6) / p.multiProcessorCount / ghz);
+  }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return 0;
