@@ -14,6 +14,7 @@ from .problem import (DiagonalHamiltonianPreconditioner, DispersiveProblem, Iden
                       create_gate, create_initial_conditions, guard_projector, lowering_operators_system,
                       multi_qudit_hamiltonian_dispersive, real_to_complex)
 from . import backend
+from . import distributed
 from .api import (discrete_adjoint, discrete_adjoint_, discrete_adjoint_batch, eval_forward, eval_forward_,
                   guard_penalty_real, infidelity, infidelity_real)
 from .backend import Handle, QGDError, get_handle, measure_fp64_peak

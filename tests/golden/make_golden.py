@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures of tests/golden/*.npz.
+
+The reference (Julia) cannot run in this image, so the fixtures are outputs of the CPU oracle
+(oracle/qgd_oracle.cpp, the restatement of the reference algorithm as written) on the named parity cases.
+They pin (i) the oracle against accidental change and (ii) the CUDA path on the GPU box without the oracle in
+the loop.  Inputs are not stored: they are regenerated from quantumgatedesign.jl_b200/configs.py (numpy
+default_rng seeds), and a checksum of the inputs is stored so that a drift of the generators is detected.
+
+    python tests/golden/make_golden.py        # rewrites tests/golden/*.npz
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def cases(q):
+    c = {}
+    c["cnot2_o4"] = q.configs.cnot2(nsteps=20, tf=20.0, gmres_tol=1e-14)
+    c["cnot3_333_o8"] = q.configs.cnot3(nsteps=12, tf=12.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=6)
+    c["cnot3_444_o8_short"] = q.configs.cnot3(nsteps=6, tf=6.0, gmres_tol=1e-14)
+    c["dense_o10"] = q.configs.dense_random(N=6, Nc=2, nsteps=8, order=10, gmres_tol=1e-14, dt_norm=0.5)
+    return c
+
+
+def input_digest(q, prob, controls, pcof, target):
+    h = hashlib.sha256()
+    for a in (np.asarray(pcof, dtype=np.float64), np.asarray(q.complex_to_real(target), dtype=np.float64),
+              np.asarray(prob.u0, dtype=np.float64), np.asarray(prob.v0, dtype=np.float64)):
+        h.update(np.ascontiguousarray(np.round(a, 12)).tobytes())
+    h.update(repr((prob.N_tot_levels, prob.N_initial_conditions, prob.nsteps, prob.tf, len(pcof))).encode())
+    return h.hexdigest()
+
+
+def main():
+    from __graft_entry__ import load_package
+    import oracle as O
+
+    q = load_package()
+    for name, (prob, controls, pcof, target, order) in cases(q).items():
+        ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+        hist = ref["history"]
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"), order=order, digest=input_digest(q, prob, controls, pcof, target),
+            grad=ref["grad"], infidelity=ref["infidelity"], guard_penalty=ref["guard_penalty"],
+            final_state=np.ascontiguousarray(hist[:, 0, -1, :]), iters_fwd=ref["iters_fwd"], iters_adj=ref["iters_adj"],
+            iters_term=ref["iters_term"])
+        print(name, "grad norm", np.linalg.norm(ref["grad"]), "infidelity", ref["infidelity"])
+
+
+if __name__ == "__main__":
+    main()

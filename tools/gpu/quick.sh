@@ -2,7 +2,7 @@
 # quick GPU check: parity tests + one bench line.  usage: bash tools/gpu/quick.sh <tag> [bench args...]
 mkdir -p gpurun_out
 tag=${1:-quick}; shift
-timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
+timeout 400 python -m pytest tests -m gpu -x -q -s > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"
 grep -E "passed|failed|error|C2 full" gpurun_out/${tag}_pytest.log | tail -8
 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 tail -3 gpurun_out/${tag}_bench.err
