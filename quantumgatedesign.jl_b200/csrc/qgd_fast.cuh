@@ -121,6 +121,7 @@ struct FastCtx {
   int lane, N, N2;
   int KT, KS;     // Krylov vectors [0,KT) live in TMEM, [KT,KT+KS) in shared memory, the rest in L2
   uint32_t tm;    // TMEM address of this warp's region (its 32 lanes, its column range)
+  static constexpr int kRingDoubles = 2 * 2 * 32 * EL;  // xs doubles as the cp.async ring of qr_solve_fast
   double2* xs;    // smem [2][32*EL]   (u,v) gather buffers (double buffered)
   double2* cv;    // smem [M+1][NC]    (p_k^(d)/d!, q_k^(d)/d!) of the current time level
   double* nullv;  // smem [N2+2]       left null vector of the residual recurrence
@@ -699,87 +700,117 @@ __device__ __forceinline__ void gs_orthogonalize(const FastCtx<EL>& c, int k, Ve
   for (; i0 < k; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 2>(c, i0, vb); gs_block<EL, BLK>(c, i0, k - i0, vb, w); }
 }
 
+// ---- asynchronous 8-byte copies L2 -> shared memory (cp.async, SASS LDGSTS) -----------------------------
+__device__ __forceinline__ void cp8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
 // Least squares  min || H y - beta e_1 ||  for the (width+1) x width Hessenberg matrix packed in c.Rg (L2), as
-// solve_least_squares! does: Givens QR, lanes own the columns j = lane + 32 s, rotation i is formed by the owner of
-// column i and applied by every lane to its columns j > i; then back substitution.  y is left in c.g (shared).
-template <int EL>
-__device__ __forceinline__ void qr_solve_fast(const FastCtx<EL>& c, int width, double beta) {
+// solve_least_squares! does: Givens QR, then back substitution; y is left in c.g (shared memory).
+// Lanes own the columns j = lane + 32 s; rotation i is formed from the pivot held by the owner of column i and
+// applied by every lane to its columns j >= i.  An L2 round trip is several rotations long, so the rows of H (and,
+// in the back substitution, the columns of R) are streamed into a small shared-memory ring by cp.async a few steps
+// ahead; the ring is indexed dynamically, so the loops stay rolled and the code small (the kernel has to fit the
+// instruction cache).  Scratch: c.xs (ring), c.hcol (1 / R[j][j]).
+template <class CTX>
+__device__ __forceinline__ void qr_solve_fast(const CTX& c, int width, double beta) {
   const int lane = c.lane;
-  constexpr int CH = 4;  // width <= restart <= 128
+  constexpr int CH = 4;                   // width <= restart <= 128
   const int nsl = (width + 31) >> 5;
-  double top[CH], nxt[CH];
+  // ring in c.xs: 4 steps x 2 column slots or 2 steps x 4 slots (256 doubles); 2 x 2 when xs only has 128 (N <= 32,
+  // where width <= 64)
+  const bool deep = nsl <= 2 && CTX::kRingDoubles >= 256;
+  const int D = deep ? 4 : 2, dmask = D - 1, RS = nsl <= 2 ? 2 : 4;
+  double* ring = reinterpret_cast<double*>(c.xs) + lane;
+  double* dinv = c.hcol;
   __syncwarp();
+  double* colp[CH];  // start of the owned columns of H
+  double top[CH];
 #pragma unroll
   for (int s = 0; s < CH; ++s) {
     const int j = lane + 32 * s;
-    const bool ok = j < width;
-    top[s] = ok ? __ldcg(c.Rg + hoff(j)) : 0.0;
-    nxt[s] = ok ? __ldcg(c.Rg + hoff(j) + 1) : 0.0;
+    colp[s] = c.Rg + hoff(j);
+    top[s] = j < width ? __ldcg(colp[s]) : 0.0;
   }
   double gcur = beta;
-  for (int i = 0; i < width; ++i) {
-    double pre[CH];
+  for (int i = -D; i < width; ++i) {  // the first D trips only fill the ring (rows 1..D)
+    if (i >= 0) {
+      if (deep) cp_wait<3>(); else cp_wait<1>();  // row i+1 has landed
+      const int so = i >> 5;
+      double a_own = top[0];
+#pragma unroll
+      for (int s = 1; s < CH; ++s) a_own = (so == s) ? top[s] : a_own;
+      const double a = __shfl_sync(FULL_MASK, a_own, i & 31);
+      const double b = c.sub[i];
+      double cs, sn;
+      givens_fast(a, b, cs, sn);
+      const double rii = cs * a + sn * b;
+      const double* rrow = ring + (((i + 1) & dmask) * RS) * 32;
+#pragma unroll
+      for (int s = 0; s < CH; ++s) {
+        const int j = lane + 32 * s;
+        if (s < nsl && j < width && j >= i) {
+          const double lo = rrow[s * 32];
+          const double r = cs * top[s] + sn * lo;
+          top[s] = -sn * top[s] + cs * lo;
+          if (j > i) colp[s][i] = r;
+        }
+      }
+      if (lane == 0) { dinv[i] = 1.0 / rii; c.g[i] = cs * gcur; }
+      gcur = -sn * gcur;
+    }
+    const int r = i + 1 + D;  // row to fetch now
+    double* wrow = ring + ((r & dmask) * RS) * 32;
 #pragma unroll
     for (int s = 0; s < CH; ++s) {
       const int j = lane + 32 * s;
-      pre[s] = (s < nsl && j < width && j > i) ? __ldcg(c.Rg + hoff(j) + i + 2) : 0.0;
+      if (s < nsl && j < width && r <= j + 1) cp8(wrow + s * 32, colp[s] + r);
     }
-    const int so = i >> 5;
-    double a_own = top[0];
-#pragma unroll
-    for (int s = 1; s < CH; ++s) a_own = (so == s) ? top[s] : a_own;
-    const double a = __shfl_sync(FULL_MASK, a_own, i & 31);
-    const double b = c.sub[i];
-    double cs, sn;
-    givens_fast(a, b, cs, sn);
-    const double rii = cs * a + sn * b;
-#pragma unroll
-    for (int s = 0; s < CH; ++s) {
-      if (s < nsl) {
-        const int j = lane + 32 * s;
-        if (j < width && j >= i) {
-          const double lo = nxt[s];
-          const double r = cs * top[s] + sn * lo;
-          top[s] = -sn * top[s] + cs * lo;
-          c.Rg[hoff(j) + i] = (j == i) ? 1.0 / rii : r;  // the back substitution only divides by the diagonal
-        }
-        nxt[s] = pre[s];
-      }
-    }
-    if (lane == 0) c.g[i] = cs * gcur;
-    gcur = -sn * gcur;
+    cp_commit();
   }
+  cp_wait<0>();
   __syncwarp();
-  // back substitution R y = g, column j-1 fetched while column j is eliminated
-  double cur[CH], nx[CH], dcur, dnxt = 0.0;
-  {
-    const double* col = c.Rg + hoff(width - 1);
+  // back substitution R y = g: right-hand side rows i = lane + 32 q in registers, column j of R through the ring
+  double gi[CH];
 #pragma unroll
-    for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; cur[q] = (q < nsl && i < width - 1) ? __ldcg(col + i) : 0.0; }
-    dcur = __ldcg(col + width - 1);
-  }
-  for (int j = width - 1; j >= 0; --j) {
-    if (j > 0) {
-      const double* col = c.Rg + hoff(j - 1);
+  for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; gi[q] = i < width ? c.g[i] : 0.0; }
+  for (int j = width - 1 + D; j >= 0; --j) {  // the first D trips only fill the ring (columns width-1 .. width-D)
+    if (j < width) {
+      if (deep) cp_wait<3>(); else cp_wait<1>();  // column j has landed
+      const int so = j >> 5;
+      double g_own = gi[0];
 #pragma unroll
-      for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; nx[q] = (q < nsl && i < j - 1) ? __ldcg(col + i) : 0.0; }
-      dnxt = __ldcg(col + j - 1);
-    }
-    const double yj = c.g[j] * dcur;  // dcur = 1 / R[j][j]
-    __syncwarp();
+      for (int q = 1; q < CH; ++q) g_own = (so == q) ? gi[q] : g_own;
+      const double yj = __shfl_sync(FULL_MASK, g_own, j & 31) * dinv[j];
+      const double* rcol = ring + ((j & dmask) * RS) * 32;
 #pragma unroll
-    for (int q = 0; q < CH; ++q) {
-      if (q < nsl) {
+      for (int q = 0; q < CH; ++q) {
         const int i = lane + 32 * q;
-        if (i < j) c.g[i] = fma(-yj, cur[q], c.g[i]);
-        else if (i == j) c.g[i] = yj;
+        if (q < nsl) {
+          if (i < j) gi[q] = fma(-yj, rcol[q * 32], gi[q]);
+          else if (i == j) gi[q] = yj;
+        }
       }
     }
-    __syncwarp();
+    const int jn = j - D;  // column to fetch now
+    if (jn >= 0) {
+      double* wcol = ring + ((jn & dmask) * RS) * 32;
+      const double* src = c.Rg + hoff(jn);
 #pragma unroll
-    for (int q = 0; q < CH; ++q) cur[q] = nx[q];
-    dcur = dnxt;
+      for (int q = 0; q < CH; ++q) {
+        const int i = lane + 32 * q;
+        if (q < nsl && i < jn) cp8(wcol + q * 32, src + i);
+      }
+    }
+    cp_commit();
   }
+  cp_wait<0>();
+#pragma unroll
+  for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; if (i < width) c.g[i] = gi[q]; }
+  __syncwarp();
 }
 
 // GMRES with the blocked orthogonalisation; same interface and iteration semantics as gmres_fast_strict.
@@ -828,7 +859,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
     __syncwarp();
     if (k == restart + 1 || cur <= tol) {
       const int width = k - 1;
-      qr_solve_fast<EL>(c, width, res_beta);
+      qr_solve_fast(c, width, res_beta);
       Vec<EL> vi;
       basis_load<EL>(c, 0, vi);
       for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 0..width-1] y
