@@ -614,7 +614,7 @@ int qgd_destroy(qgd_handle_t* h) {
   DevBuf* bufs[] = {&h->d_blob, &h->d_minv[0], &h->d_minv[1], &h->d_u0, &h->d_v0, &h->d_ctrls, &h->d_aux, &h->d_table, &h->d_pcof,
                     &h->d_cvals, &h->d_history, &h->d_final, &h->d_final_all, &h->d_terminal, &h->d_lambda0, &h->d_lamhist,
                     &h->d_gradcol, &h->d_grad, &h->d_guardcol, &h->d_guard, &h->d_infid, &h->d_iters_f, &h->d_iters_a,
-                    &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch, &h->d_counter};
+                    &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch, &h->d_counter, &h->d_progress, &h->d_carry};
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);

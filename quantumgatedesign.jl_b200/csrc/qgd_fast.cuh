@@ -918,6 +918,38 @@ __device__ __forceinline__ size_t next_item(unsigned int* counter, int lane) {
   return (size_t)__shfl_sync(FULL_MASK, v, 0);
 }
 
+// ---- time-sliced work queue -----------------------------------------------------------------------------
+// A column's time loop is strictly sequential, but nothing except one state vector (and, in the adjoint sweep, the
+// gradient partial) is carried from one time step to the next.  The sweeps therefore hand out TICKETS of
+// `seg_steps` time steps: ticket t = (segment t / items, item t % items).  A warp that draws a ticket waits until
+// the previous segment of that item has been published (it was drawn earlier, so it is finished or running on a
+// resident warp: no deadlock), continues the item for seg_steps steps and publishes it again.  Columns thereby
+// migrate between warps and the idle tail at the end of a sweep shrinks from one whole column to one segment.
+template <int EL>
+__device__ __forceinline__ void vload_cg(Vec<EL>& a, const double* p, int N, int lane) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) {
+    const int r = lane + 32 * e;
+    const bool ok = r < N;
+    a.u[e] = ok ? __ldcg(p + r) : 0.0;
+    a.v[e] = ok ? __ldcg(p + N + r) : 0.0;
+  }
+}
+__device__ __forceinline__ void wait_segment(const int* progress, int seg, int lane) {
+  if (lane == 0) {
+    const volatile int* f = progress;
+    unsigned spins = 0;
+    while (*f < seg && ++spins < (1u << 27)) __nanosleep(256);  // the bound only turns a logic error into wrong numbers instead of a hang
+  }
+  __syncwarp();
+  __threadfence();
+}
+__device__ __forceinline__ void publish_segment(int* progress, int seg, int lane) {
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(progress, seg + 1);
+}
+
 // control Taylor coefficients of a time level: global [2][M+1][NC] -> shared (p, q) pairs [M+1][NC]
 template <int EL, int M, int NC>
 __device__ __forceinline__ void load_cv_fast(const FastCtx<EL>& c, const double* src) {
@@ -972,34 +1004,44 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
   const size_t cv_stride = (size_t)2 * (M + 1) * NC;
   const size_t slot_sz = (size_t)N2 * (M + 1);
   const FwdOpFast<EL, M, NC> op{c, R, a_lhs};
-  // columns need different numbers of GMRES iterations: warps draw (control vector, column) items from a queue
-  for (size_t item = next_item(a.work_counter, lane); item < items; item = next_item(a.work_counter, lane)) {
+  // columns need different numbers of GMRES iterations: warps draw (segment, control vector, column) tickets
+  const int S = a.seg_steps, nseg = (d.nsteps + S - 1) / S;
+  const size_t tickets = items * (size_t)nseg;
+  for (size_t ticket = next_item(a.work_counter, lane); ticket < tickets; ticket = next_item(a.work_counter, lane)) {
+    const int seg = (int)(ticket / items);
+    const size_t item = ticket % items;
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
     const double* cvb = a.cvals + (size_t)b * (d.nsteps + 1) * cv_stride;
     double* hist = a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b);
+    double* carry = a.final_state + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b);  // state between segments; w_N at the end
+    const int n0 = seg * S, n1 = min(n0 + S, d.nsteps);
+    const bool last = seg == nseg - 1;
     Vec<EL> x;
+    if (seg == 0) {
 #pragma unroll
-    for (int e = 0; e < EL; ++e) {
-      const int r = lane + 32 * e;
-      x.u[e] = r < N ? d.u0[r + (size_t)N * col] : 0.0;
-      x.v[e] = r < N ? d.v0[r + (size_t)N * col] : 0.0;
+      for (int e = 0; e < EL; ++e) {
+        const int r = lane + 32 * e;
+        x.u[e] = r < N ? d.u0[r + (size_t)N * col] : 0.0;
+        x.v[e] = r < N ? d.v0[r + (size_t)N * col] : 0.0;
+      }
+    } else {
+      wait_segment(a.progress + item, seg, lane);
+      vload_cg(x, carry, N, lane);
     }
-    load_cv_fast<EL, M, NC>(c, cvb);
-    for (int n = 0; n < d.nsteps; ++n) {
+    load_cv_fast<EL, M, NC>(c, cvb + (size_t)n0 * cv_stride);
+    const int nend = last ? n1 : n1 - 1;  // the last segment also forms the Taylor columns at the final time (forward_evolution.jl:232-242)
+    for (int n = n0; n <= nend; ++n) {
       Vec<EL> rhs, guess;
       double* slot = (n % a.save_every == 0) ? hist + slot_sz * (n / a.save_every) : nullptr;
       fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, rhs, a_tay, &guess, slot);      // explicit part at t_n
+      if (n == d.nsteps) break;
       load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n + 1) * cv_stride);              // implicit part uses t_{n+1}
       x = guess;
       const int it = gmres_fast<EL, NC>(c, R, op, x, rhs, d.abstol, N2, N2);
       if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
     }
-    {  // Taylor columns at the final time (forward_evolution.jl:232-242)
-      Vec<EL> dummy, guess;
-      double* slot = (d.nsteps % a.save_every == 0) ? hist + slot_sz * (d.nsteps / a.save_every) : nullptr;
-      fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, dummy, a_tay, &guess, slot);
-      vstore(x, a.final_state + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b), N, lane);
-    }
+    vstore(x, carry, N, lane);
+    publish_segment(a.progress + item, seg, lane);
   }
   if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }
@@ -1047,17 +1089,30 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
   double* gSs = gKs + M * NC;    // [M][NC] reduced g^S
   const AdjOpFast<EL, M, NC> op{c, R, a_lhs};
   const double fsc = -2.0 * d.dt / d.tf;
-  for (size_t item = next_item(a.work_counter, lane); item < items; item = next_item(a.work_counter, lane)) {
+  const int S = a.seg_steps, nseg = (d.nsteps + S - 1) / S;
+  const size_t tickets = items * (size_t)nseg;
+  for (size_t ticket = next_item(a.work_counter, lane); ticket < tickets; ticket = next_item(a.work_counter, lane)) {
+    const int seg = (int)(ticket / items);
+    const size_t item = ticket % items;
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
     const double* cvb = a.cvals + (size_t)b * Nt * cv_stride;
     const double* hist = a.history + slot_sz * Nt * ((size_t)cl + (size_t)d.ncol * b);
     double* lam0 = a.lambda0 ? a.lambda0 + (size_t)N2 * Nt * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
-    for (int t = lane; t < P; t += 32) gacc[t] = 0.0;
+    double* gcol = a.gradcol + (size_t)P * ((size_t)cl + (size_t)d.ncol * b);  // gradient partial, also carried between segments
+    double* carry = a.carry + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b);   // lambda between segments
+    const int n_hi = d.nsteps - 1 - seg * S, n_lo = max(n_hi - S + 1, 0);
     Vec<EL> lam;
-    vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
-    if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, lane);
-    load_cv_fast<EL, M, NC>(c, cvb + (size_t)d.nsteps * cv_stride);
-    for (int n = d.nsteps - 1; n >= 0; --n) {
+    if (seg == 0) {
+      for (int t = lane; t < P; t += 32) gacc[t] = 0.0;
+      vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
+      if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, lane);
+    } else {
+      wait_segment(a.progress + item, seg, lane);
+      for (int t = lane; t < P; t += 32) gacc[t] = __ldcg(gcol + t);
+      vload_cg(lam, carry, N, lane);
+    }
+    load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n_hi + 1) * cv_stride);
+    for (int n = n_hi; n >= n_lo; --n) {
       double gK[M][NC], gS[M][NC];
       Vec<EL> w0, rhs;
       // ---- implicit side: time level n+1 (its control values are the ones currently loaded)
@@ -1108,8 +1163,9 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       }
     }
     __syncwarp();
-    for (int t = lane; t < P; t += 32) a.gradcol[(size_t)t + (size_t)P * ((size_t)cl + (size_t)d.ncol * b)] = gacc[t];
-    __syncwarp();
+    for (int t = lane; t < P; t += 32) gcol[t] = gacc[t];
+    if (seg < nseg - 1) vstore(lam, carry, N, lane);
+    publish_segment(a.progress + item, seg, lane);
   }
   if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }

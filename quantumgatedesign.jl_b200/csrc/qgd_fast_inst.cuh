@@ -61,6 +61,15 @@ void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, Sw
   h->d_counter.reserve(64);
   CUDA_CHECK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
   a.work_counter = h->d_counter.as<unsigned int>();
+  // time-sliced tickets: about 24 segments per column, published through d_progress
+  const size_t items = (size_t)a.B * h->ncol;
+  const int nsteps = (int)h->nsteps;
+  a.seg_steps = getenv("QGD_SEG_STEPS") ? std::max(1, atoi(getenv("QGD_SEG_STEPS"))) : std::max(1, (nsteps + 23) / 24);
+  h->d_progress.reserve(std::max<size_t>(items, 1) * 4);
+  CUDA_CHECK(cudaMemsetAsync(h->d_progress.p, 0, std::max<size_t>(items, 1) * 4, h->stream));
+  a.progress = h->d_progress.as<int>();
+  h->d_carry.reserve(std::max<size_t>(items, 1) * (size_t)h->N2 * 8);
+  a.carry = h->d_carry.as<double>();
   a.ks = L.ks; a.kt = L.kt; a.tmem_cols = L.tmem_cols;
   a.warp_smem_doubles = L.warp_doubles;
 }

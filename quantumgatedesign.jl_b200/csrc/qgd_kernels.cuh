@@ -24,7 +24,10 @@ struct SweepArgs {
   int ks;                // fast path: Krylov basis vectors resident in shared memory per warp
   int kt;                // fast path: Krylov basis vectors resident in tensor memory per warp
   int tmem_cols;         // fast path: TMEM columns the CTA allocates (0: none; power of two >= 32)
-  unsigned int* work_counter;  // fast path: item queue head (zeroed before the launch)
+  unsigned int* work_counter;  // fast path: ticket queue head (zeroed before the launch)
+  int seg_steps;         // fast path: time steps per ticket
+  int* progress;         // fast path: [items] segments published per item (zeroed before the launch)
+  double* carry;         // fast path, adjoint sweep: [2N][ncol][B] lambda between segments
   const double* cvals;   // [B][nsteps+1][2][m+1][Nc]
   double* history;       // [2N][1+m][nslots][ncol][B]
   double* final_state;   // [2N][ncol][B]
