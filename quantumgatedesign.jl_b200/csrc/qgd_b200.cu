@@ -107,7 +107,7 @@ using namespace qgd;
 int pick_el(int N) {
   int el = 1;
   while (32 * el < N) el *= 2;
-  if (el > 4) throw QgdError(QGD_EUNSUPPORTED, "N_tot_levels > 128 is not supported by the warp-per-column kernels yet (dense large-N path: see DESIGN.md)");
+  if (el > 8) throw QgdError(QGD_EUNSUPPORTED, "N_tot_levels > 256 is not supported by the warp-per-column kernels (see DESIGN.md)");
   return el;
 }
 
@@ -420,7 +420,8 @@ void compute_cvals(qgd_handle* h, int m, int B, const double* d_pcof) {
   switch (el) {                                   \
     case 1: NAME##_1(__VA_ARGS__); break;         \
     case 2: NAME##_2(__VA_ARGS__); break;         \
-    default: NAME##_4(__VA_ARGS__); break;        \
+    case 4: NAME##_4(__VA_ARGS__); break;         \
+    default: NAME##_8(__VA_ARGS__); break;        \
   }
 
 void h2d(qgd_handle* h, void* dst, const void* src, size_t bytes) {

@@ -91,6 +91,7 @@ struct qgd_handle {
 QGD_DECLARE_LAUNCHERS(1)
 QGD_DECLARE_LAUNCHERS(2)
 QGD_DECLARE_LAUNCHERS(4)
+QGD_DECLARE_LAUNCHERS(8)
 
 // Register-operator kernels (qgd_fast.cuh), one translation unit per Taylor depth M = order/2.  Each launcher
 // returns false when the (levels-per-lane, operator count) shape was not built; the caller then uses the
