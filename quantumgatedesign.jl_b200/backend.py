@@ -16,7 +16,8 @@ from ._abi import c_double_p, c_int64_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libqgd_b200.so")
+# QGD_B200_LIB selects another build of the same library (A/B runs of kernel variants during development)
+LIB_PATH = os.environ.get("QGD_B200_LIB") or os.path.join(CSRC, "libqgd_b200.so")
 _LIB = None
 
 EXPORTS = [

@@ -34,6 +34,15 @@ namespace qgd {
 #ifndef QGD_MGS_BLOCK
 #define QGD_MGS_BLOCK 8
 #endif
+// Per-kernel code-shape switches of the blocked orthogonalisation, chosen by measurement:
+// bit 0 = the three basis tiers share one copy of the block arithmetic (smaller code: the adjoint kernel's hot
+// loop then fits the 32 KB instruction cache), bit 1 = block reduction through shared memory instead of shuffles.
+#ifndef QGD_FWD_VARIANT
+#define QGD_FWD_VARIANT 2
+#endif
+#ifndef QGD_BWD_VARIANT
+#define QGD_BWD_VARIANT 3
+#endif
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
@@ -56,12 +65,23 @@ __device__ __forceinline__ double warp_allsum(double p) {
 #endif
 }
 
+#ifndef QGD_DOT_CHAIN
+#define QGD_DOT_CHAIN 0  // 1: one FMA chain per dot product (2 EL instructions) instead of two chains and an add (2 EL + 1)
+#endif
 template <int EL>
 __device__ __forceinline__ double vdot_local(const Vec<EL>& a, const Vec<EL>& b) {
+#if QGD_DOT_CHAIN
+  double s = a.u[0] * b.u[0];
+  s = fma(a.v[0], b.v[0], s);
+#pragma unroll
+  for (int e = 1; e < EL; ++e) { s = fma(a.u[e], b.u[e], s); s = fma(a.v[e], b.v[e], s); }
+  return s;
+#else
   double s0 = a.u[0] * b.u[0], s1 = a.v[0] * b.v[0];
 #pragma unroll
   for (int e = 1; e < EL; ++e) { s0 = fma(a.u[e], b.u[e], s0); s1 = fma(a.v[e], b.v[e], s1); }
   return s0 + s1;
+#endif
 }
 
 // ---- per-lane operator registers ---------------------------------------------------------------------
@@ -121,8 +141,10 @@ struct FastCtx {
   int lane, N, N2;
   int KT, KS;     // Krylov vectors [0,KT) live in TMEM, [KT,KT+KS) in shared memory, the rest in L2
   uint32_t tm;    // TMEM address of this warp's region (its 32 lanes, its column range)
-  static constexpr int kRingDoubles = 2 * 2 * 32 * EL;  // xs doubles as the cp.async ring of qr_solve_fast
-  double2* xs;    // smem [2][32*EL]   (u,v) gather buffers (double buffered)
+  // xs: (u,v) gather buffers of the operator application (double buffered, 2 x 32 EL double2); the same storage is
+  // the 8 x 32 transposition buffer of block_allsum and the cp.async ring of qr_solve_fast (>= 256 doubles)
+  static constexpr int kRingDoubles = 2 * 2 * 32 * EL < 256 ? 256 : 2 * 2 * 32 * EL;
+  double2* xs;    // smem [kRingDoubles / 2]
   double2* cv;    // smem [M+1][NC]    (p_k^(d)/d!, q_k^(d)/d!) of the current time level
   double* nullv;  // smem [N2+2]       left null vector of the residual recurrence
   double2* rot;   // smem [N2+2+8]     rot[0] = (1,0); rot[i+1] = Givens (cs, sn) of rotation i   (strict path)
@@ -136,7 +158,7 @@ struct FastCtx {
 template <int EL, int M, int NC>
 __host__ __device__ constexpr int fast_fixed_doubles(int N2) {
   // xs + cv + nullv + rot + g
-  return 2 * 2 * 32 * EL + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
+  return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
 }
 
 template <int EL>
@@ -192,7 +214,7 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
   vscale(out, alpha[0]);
   if (STEP) {
     *guess = x;
-    if (hist) vstore(x, hist, N, lane);
+    if (hist) vstore_cs(x, hist, N, lane);
   }
   __syncwarp();
 #pragma unroll
@@ -204,7 +226,7 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
       vaxpy(out, alpha[i], w);
       if (STEP) {
         vaxpy(*guess, a_tay[i], w);
-        if (hist) vstore(w, hist + (size_t)i * N2, N, lane);
+        if (hist) vstore_cs(w, hist + (size_t)i * N2, N, lane);
       }
     }
     double2* xb = c.xs + (i & 1) * 32 * EL;
@@ -236,7 +258,7 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
     vaxpy(out, alpha[M], w);
     if (STEP) {
       vaxpy(*guess, a_tay[M], w);
-      if (hist) vstore(w, hist + (size_t)M * N2, N, lane);
+      if (hist) vstore_cs(w, hist + (size_t)M * N2, N, lane);
     }
   }
 }
@@ -255,7 +277,7 @@ __device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, 
   Vec<EL> wh[M];
   if (GRAD) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) vload(wh[i], hist + (size_t)i * N2, N, lane);
+    for (int i = 0; i < M; ++i) vload_cs(wh[i], hist + (size_t)i * N2, N, lane);
   }
   __syncwarp();
 #pragma unroll
@@ -622,6 +644,30 @@ __device__ __forceinline__ void block_allsum(double (&p)[BLK], double* slot, int
   for (int q = 0; q < BLK; q += 2) { const double2 t = reinterpret_cast<const double2*>(slot)[q >> 1]; p[q] = t.x; p[q + 1] = t.y; }
 }
 
+// Same result through shared memory (variant bit 1): the 8 x 32 partials are transposed through the
+// (idle) gather buffer instead of three select-and-shuffle stages -- 8 STS.64 + 8 LDS.64 + 7 DADD instead of
+// 28 selects + 14 SHFL + 7 DADD per block, and two shared-memory round trips shorter.  Value q of lane l sits at
+// T[32 q + (l ^ 4 (q & 3))]: stores are a permutation of a row, and the reader of value qv = lane / 4, s = lane % 4
+// (which sums the partials of lanes 4 t + s, t = 0..7) hits 16 distinct 8-byte banks per half warp.
+__device__ __forceinline__ void block_allsum8_smem(double (&p)[8], double* T, double* slot, int lane) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) T[32 * q + (lane ^ (4 * (q & 3)))] = p[q];
+  __syncwarp();
+  const int qv = lane >> 2, s = lane & 3;
+  const double* row = T + 32 * qv + s;
+  const int sw = qv & 3;
+  double a[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) a[t] = row[4 * (t ^ sw)];
+  const double r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  double c0, c1;
+  dmma884(c0, c1, 1.0, r);  // lane l: totals of values 2(l%4), 2(l%4)+1
+  if (lane < 4) reinterpret_cast<double2*>(slot)[lane] = make_double2(c0, c1);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) { const double2 t = reinterpret_cast<const double2*>(slot)[q >> 1]; p[q] = t.x; p[q + 1] = t.y; }
+}
+
 // tcgen05.ld of N consecutive 32-bit columns of this warp's 32 TMEM lanes (issue only)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -679,25 +725,39 @@ __device__ __forceinline__ void gs_load_block(const FastCtx<EL>& c, int i0, Vec<
 
 // One block: h_q = <v_{i0+q}, w> for the whole block from the same w, then w -= sum_{q < nb} h_q v_{i0+q}.
 // The coefficients are left in c.hcol[i0 .. i0+BLK).
-template <int EL, int BLK>
+template <int EL, int BLK, int VARIANT>
 __device__ __forceinline__ void gs_block(const FastCtx<EL>& c, int i0, int nb, const Vec<EL> (&vb)[BLK], Vec<EL>& w) {
   double h[BLK];
 #pragma unroll
   for (int q = 0; q < BLK; ++q) h[q] = vdot_local<EL>(vb[q], w);
-  block_allsum<BLK>(h, c.hcol + i0, c.lane);
+  if constexpr (BLK == 8 && (VARIANT & 2) != 0) block_allsum8_smem(h, reinterpret_cast<double*>(c.xs), c.hcol + i0, c.lane);
+  else block_allsum<BLK>(h, c.hcol + i0, c.lane);
 #pragma unroll
   for (int q = 0; q < BLK; ++q)
     if (q < nb) vaxpy(w, -h[q], vb[q]);
 }
 
 // w is orthogonalised against V[:, 0..k-1]; c.hcol[0..k-1] receives the coefficients.
-template <int EL, int BLK>
+template <int EL, int BLK, int VARIANT>
 __device__ __forceinline__ void gs_orthogonalize(const FastCtx<EL>& c, int k, Vec<EL>& w) {
+  __syncwarp();  // the gather buffer (read by the operator application) becomes the transposition buffer
+  if constexpr ((VARIANT & 1) != 0) {
+  // one copy of the block arithmetic for the three tiers: the hot loop has to fit the 32 KB instruction cache
+  const int bT = c.KT, bS = c.KT + c.KS;
+  for (int i0 = 0; i0 < k; i0 += BLK) {
+    Vec<EL> vb[BLK];
+    if (i0 < bT) gs_load_block<EL, BLK, 0>(c, i0, vb);
+    else if (i0 < bS) gs_load_block<EL, BLK, 1>(c, i0, vb);
+    else gs_load_block<EL, BLK, 2>(c, i0, vb);
+    gs_block<EL, BLK, VARIANT>(c, i0, k - i0, vb, w);
+  }
+  } else {
   const int eT = min(k, c.KT), eS = min(k, c.KT + c.KS);
   int i0 = 0;
-  for (; i0 < eT; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 0>(c, i0, vb); gs_block<EL, BLK>(c, i0, k - i0, vb, w); }
-  for (; i0 < eS; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 1>(c, i0, vb); gs_block<EL, BLK>(c, i0, k - i0, vb, w); }
-  for (; i0 < k; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 2>(c, i0, vb); gs_block<EL, BLK>(c, i0, k - i0, vb, w); }
+  for (; i0 < eT; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 0>(c, i0, vb); gs_block<EL, BLK, VARIANT>(c, i0, k - i0, vb, w); }
+  for (; i0 < eS; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 1>(c, i0, vb); gs_block<EL, BLK, VARIANT>(c, i0, k - i0, vb, w); }
+  for (; i0 < k; i0 += BLK) { Vec<EL> vb[BLK]; gs_load_block<EL, BLK, 2>(c, i0, vb); gs_block<EL, BLK, VARIANT>(c, i0, k - i0, vb, w); }
+  }
 }
 
 // ---- asynchronous 8-byte copies L2 -> shared memory (cp.async, SASS LDGSTS) -----------------------------
@@ -814,7 +874,7 @@ __device__ __forceinline__ void qr_solve_fast(const CTX& c, int width, double be
 }
 
 // GMRES with the blocked orthogonalisation; same interface and iteration semantics as gmres_fast_strict.
-template <int EL, int NC, class OP>
+template <int EL, int NC, int VARIANT, class OP>
 __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
                                   int restart, int maxiter) {
   constexpr int BLK = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 4;
@@ -828,36 +888,52 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
   double rbeta = rsqrt(beta2), beta = beta2 * rbeta;
   vscale(v, rbeta);
   basis_store<EL>(c, 0, v);
-  double cur = beta, res_beta = beta, accum = 1.0;
+  double res_beta = beta, accum = 1.0;
+  // residual estimate beta / sqrt(accum) against tol, tested as beta^2 <= tol^2 accum (no square root on the
+  // critical path of an iteration; the two tests differ only when the estimate is within an ulp of tol)
+  const double tol2 = tol * tol;
+  double res_beta2 = beta2;
+  bool conv = !(res_beta2 > tol2);
   __syncwarp();
   if (lane == 0) c.nullv[0] = 1.0;
   __syncwarp();
   int k = 1, it = 0;
-  while (it < maxiter && cur > tol) {
+  constexpr int CHK = 2 * EL;  // k <= restart <= 2N <= 64 EL: CHK chunks of 32 rows cover a Hessenberg column
+  while (it < maxiter && !conv) {
     op.apply(v, w);  // expand!
     precond_fast<EL, NC>(R, w);
-    gs_orthogonalize<EL, BLK>(c, k, w);
+    gs_orthogonalize<EL, BLK, VARIANT>(c, k, w);
     // ||w||^2 and the null-vector recurrence <nullvec[0..k), H[0..k, k-1]> (update_residual!)
-    double dpart = 0.0;
-    for (int i = lane; i < k; i += 32) dpart = fma(c.nullv[i], c.hcol[i], dpart);
+    double dpart = 0.0, hreg[CHK];
+#pragma unroll
+    for (int s = 0; s < CHK; ++s) {
+      const int i = lane + 32 * s;
+      const bool ok = i < k;
+      hreg[s] = ok ? c.hcol[i] : 0.0;
+      const double nl = ok ? c.nullv[i] : 0.0;
+      dpart = fma(nl, hreg[s], dpart);
+    }
     const double nrm2 = warp_allsum(vdot_local<EL>(w, w));
     const double dsum = warp_allsum(dpart);
     const double rnrm = rsqrt(nrm2), nrm = nrm2 * rnrm;
     vscale(w, rnrm);
     basis_store<EL>(c, k, w);
+    const double nv = -(dsum * rnrm);
     {  // Hessenberg column k-1 (rows 0..k) to the packed matrix in L2
       double* hc = c.Rg + hoff(k - 1);
-      for (int i = lane; i < k; i += 32) hc[i] = c.hcol[i];
-      if (lane == 0) { hc[k] = nrm; c.sub[k - 1] = nrm; }
+#pragma unroll
+      for (int s = 0; s < CHK; ++s) {
+        const int i = lane + 32 * s;
+        if (i < k) hc[i] = hreg[s];
+      }
+      if (lane == 0) { hc[k] = nrm; c.sub[k - 1] = nrm; c.nullv[k] = nv; }
     }
-    const double nv = -(dsum * rnrm);
-    if (lane == 0) c.nullv[k] = nv;
     accum = fma(nv, nv, accum);
-    cur = res_beta * rsqrt(accum);
+    conv = !(res_beta2 > tol2 * accum);
     k += 1;
     v = w;
     __syncwarp();
-    if (k == restart + 1 || cur <= tol) {
+    if (k == restart + 1 || conv) {
       const int width = k - 1;
       qr_solve_fast(c, width, res_beta);
       Vec<EL> vi;
@@ -869,7 +945,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
         if (j + 1 < width) vi = vn;
       }
       k = 1;
-      if (cur > tol) {  // restart (residual.current keeps its value, as in the package)
+      if (!conv) {  // restart (residual.current keeps its value, as in the package)
         op.apply(x, w);
 #pragma unroll
         for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
@@ -878,7 +954,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
         rbeta = rsqrt(beta2); beta = beta2 * rbeta;
         vscale(v, rbeta);
         basis_store<EL>(c, 0, v);
-        accum = 1.0; res_beta = beta;
+        accum = 1.0; res_beta = beta; res_beta2 = beta2;
         __syncwarp();
         if (lane == 0) c.nullv[0] = 1.0;
       }
@@ -889,10 +965,10 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
   return it;
 }
 
-template <int EL, int NC, class OP>
+template <int EL, int NC, int VARIANT, class OP>
 __device__ __forceinline__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b,
                                           double tol, int restart, int maxiter) {
-  if constexpr (QGD_MGS_BLOCK > 1) return gmres_fast_blocked<EL, NC, OP>(c, R, op, x, b, tol, restart, maxiter);
+  if constexpr (QGD_MGS_BLOCK > 1) return gmres_fast_blocked<EL, NC, VARIANT, OP>(c, R, op, x, b, tol, restart, maxiter);
   else return gmres_fast_strict<EL, NC, OP>(c, R, op, x, b, tol, restart, maxiter);
 }
 
@@ -973,7 +1049,7 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   c.KT = a.kt;
   c.tm = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cols * (warp >> 2));
   double* w = reinterpret_cast<double*>(smem + 16) + (size_t)warp * a.warp_smem_doubles;
-  c.xs = reinterpret_cast<double2*>(w); w += 2 * 2 * 32 * EL;
+  c.xs = reinterpret_cast<double2*>(w); w += FastCtx<EL>::kRingDoubles;
   c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
   c.rot = reinterpret_cast<double2*>(w); c.hcol = w; c.sub = w + d.N2 + 10; w += 2 * (d.N2 + 2 + 8);
   c.nullv = w; w += d.N2 + 2;
@@ -1037,7 +1113,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
       if (n == d.nsteps) break;
       load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n + 1) * cv_stride);              // implicit part uses t_{n+1}
       x = guess;
-      const int it = gmres_fast<EL, NC>(c, R, op, x, rhs, d.abstol, N2, N2);
+      const int it = gmres_fast<EL, NC, QGD_FWD_VARIANT>(c, R, op, x, rhs, d.abstol, N2, N2);
       if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
     }
     vstore(x, carry, N, lane);
@@ -1150,14 +1226,14 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       __syncwarp();
       if (n >= 1) {
         // guard forcing f_n = -(2 dt/tf) W w_n (interior point: trapezoid weight 1), W diagonal
-        vload(w0, hist + slot_sz * n, N, lane);
+        vload_cs(w0, hist + slot_sz * n, N, lane);
 #pragma unroll
         for (int e = 0; e < EL; ++e) {
           rhs.u[e] = fma(fsc, R.wu[e] * w0.u[e], rhs.u[e]);
           rhs.v[e] = fma(fsc, R.wv[e] * w0.v[e], rhs.v[e]);
         }
         // x0 = lambda_{n+1} (forward_evolution.jl:450)
-        const int it = gmres_fast<EL, NC>(c, R, op, lam, rhs, d.abstol, N2, N2);
+        const int it = gmres_fast<EL, NC, QGD_BWD_VARIANT>(c, R, op, lam, rhs, d.abstol, N2, N2);
         if (lam0) vstore(lam, lam0 + (size_t)N2 * n, N, lane);
         if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
       }

@@ -50,14 +50,16 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   return L;
 }
 
+// The Krylov tail and the packed Hessenberg matrices of all resident warps live in ONE allocation (d_V) so that a
+// single L2 access-policy window can cover them (launch_sweep below).
 void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, SweepArgs& a) {
   const size_t warps = (size_t)L.grid * L.wpc;
   a.v_stride = (size_t)(std::max(restart + 1 - L.ks - L.kt, 1) + QGD_MGS_BLOCK) * 2 * 32 * el;
   a.h_stride = (size_t)restart * (restart + 3) / 2 + 2;
-  h->d_V.reserve(warps * a.v_stride * 8);
-  h->d_H.reserve(warps * a.h_stride * 8);
+  const size_t v_bytes = (warps * a.v_stride * 8 + 255) & ~(size_t)255;
+  h->d_V.reserve(v_bytes + warps * a.h_stride * 8);
   a.Vws = h->d_V.as<double>();
-  a.Hws = h->d_H.as<double>();
+  a.Hws = reinterpret_cast<double*>(h->d_V.as<unsigned char>() + v_bytes);
   h->d_counter.reserve(64);
   CUDA_CHECK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
   a.work_counter = h->d_counter.as<unsigned int>();
@@ -74,22 +76,50 @@ void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, Sw
   a.warp_smem_doubles = L.warp_doubles;
 }
 
+// Launch a sweep kernel with an L2 access-policy window over the Krylov / Hessenberg workspace: those lines are
+// rewritten by every solve and should stay in the L2 while the state history streams through it (the history itself
+// is accessed with evict-first loads and stores).  QGD_L2_PERSIST=0 launches without the window.
+template <class... KArgs, class... Args>
+void launch_sweep(qgd_handle* h, void (*kernel)(KArgs...), const FastCfg& L, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)L.grid); cfg.blockDim = dim3((unsigned)L.threads);
+  cfg.dynamicSmemBytes = L.smem; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  int n = 0;
+  const char* env = getenv("QGD_L2_PERSIST");
+  const size_t carve = (size_t)std::max(h->prop.persistingL2CacheMaxSize, 0);
+  const size_t max_win = (size_t)std::max(h->prop.accessPolicyMaxWindowSize, 0);
+  if (!(env && atoi(env) == 0) && carve > 0 && max_win > 0 && h->d_V.cap > 0) {
+    if (!h->l2_carved) {
+      CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+      h->l2_carved = true;
+    }
+    const size_t bytes = std::min(h->d_V.cap, max_win);
+    at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[0].val.accessPolicyWindow.base_ptr = h->d_V.p;
+    at[0].val.accessPolicyWindow.num_bytes = bytes;
+    at[0].val.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
+    at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    n = 1;
+  }
+  cfg.attrs = at; cfg.numAttrs = (unsigned)n;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, args...));
+  h->stats.kernel_launches++;
+}
+
 template <int EL, int M, int NC>
 void launch_forward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   FastCfg L = plan_fast(h, k_forward_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)a.B * d.ncol, 0, d.N2);
   ensure_krylov_fast(h, L, EL, d.N2, a);
-  k_forward_fast<EL, M, NC><<<L.grid, L.threads, L.smem, h->stream>>>(d, a);
-  CUDA_CHECK(cudaGetLastError());
-  h->stats.kernel_launches++;
+  launch_sweep(h, k_forward_fast<EL, M, NC>, L, d, a);
 }
 template <int EL, int M, int NC>
 void launch_backward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   const int extra = d.P + 2 * M * NC;
   FastCfg L = plan_fast(h, k_backward_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)a.B * d.ncol, extra, d.N2);
   ensure_krylov_fast(h, L, EL, d.N2, a);
-  k_backward_fast<EL, M, NC><<<L.grid, L.threads, L.smem, h->stream>>>(d, a, h->d_ctrls.as<QgdDevControl>());
-  CUDA_CHECK(cudaGetLastError());
-  h->stats.kernel_launches++;
+  launch_sweep(h, k_backward_fast<EL, M, NC>, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
 }
 template <int EL, int M, int NC>
 void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, int ncols, const double* cv, int adjoint) {

@@ -75,6 +75,7 @@ struct qgd_handle {
   // register-operator fast path (qgd_fast.cuh): structure test done once at creation
   bool fast_ok = false;
   int fast_el = 0;
+  bool l2_carved = false;  // cudaLimitPersistingL2CacheSize set for the workspace window (qgd_fast_inst.cuh)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   qgd_stats_t stats{};
 };

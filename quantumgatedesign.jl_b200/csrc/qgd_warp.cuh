@@ -99,6 +99,38 @@ __device__ __forceinline__ void vstore(const Vec<EL>& a, double* p, int N, int l
     if (r < N) { p[r] = a.u[e]; p[N + r] = a.v[e]; }
   }
 }
+// Streaming (evict-first) variants for the state history: it is written once by the forward sweep and read once by
+// the adjoint sweep, and must not push the L2-resident Krylov / Hessenberg workspaces out of the cache.
+#ifndef QGD_HIST_CS
+#define QGD_HIST_CS 1
+#endif
+template <int EL>
+__device__ __forceinline__ void vload_cs(Vec<EL>& a, const double* p, int N, int lane) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) {
+    int r = lane + 32 * e;
+    bool ok = r < N;
+#if QGD_HIST_CS
+    a.u[e] = ok ? __ldcs(p + r) : 0.0;
+    a.v[e] = ok ? __ldcs(p + N + r) : 0.0;
+#else
+    a.u[e] = ok ? p[r] : 0.0;
+    a.v[e] = ok ? p[N + r] : 0.0;
+#endif
+  }
+}
+template <int EL>
+__device__ __forceinline__ void vstore_cs(const Vec<EL>& a, double* p, int N, int lane) {
+#pragma unroll
+  for (int e = 0; e < EL; ++e) {
+    int r = lane + 32 * e;
+#if QGD_HIST_CS
+    if (r < N) { __stcs(p + r, a.u[e]); __stcs(p + N + r, a.v[e]); }
+#else
+    if (r < N) { p[r] = a.u[e]; p[N + r] = a.v[e]; }
+#endif
+  }
+}
 
 // (K_k x_v, K_k x_u, S_k x_u, S_k x_v)[row r] for operator k from a vector in shared memory.
 __device__ __forceinline__ void op_zsums(const WarpCtx& c, int k, int r, const double* x, double& zKu, double& zKv,
