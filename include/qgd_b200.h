@@ -131,6 +131,24 @@ int qgd_eval_forward(qgd_handle_t *h, const double *pcof, int64_t n_batch, int32
                      int64_t save_every, double *history, double *final_state,
                      int64_t *gmres_iters);
 
+/* eval_forward! with the `forcing` keyword (src/forward_evolution.jl:33-37, 118-129, 167-206): the forcing enters the
+ * Taylor recursion at t_n (compute_derivatives!(...; forcing_matrix), src/hermite.jl:91-95) and, being explicit, the
+ * implicit-side combination of the forcing at t_{n+1} is moved to the right-hand side; the Taylor columns stored for
+ * the final time are computed WITHOUT forcing, as the reference does (:232-236).
+ *   forcing [2N, m, 1+nsteps, ncol, n_batch]; other arguments as qgd_eval_forward. */
+int qgd_eval_forward_forced(qgd_handle_t *h, const double *pcof, int64_t n_batch, int32_t order,
+                            int64_t save_every, const double *forcing, double *history,
+                            double *final_state, int64_t *gmres_iters);
+
+/* eval_grad_forced (src/eval_grad_forced.jl:18-195), cost_type = :Infidelity: the gradient by differentiating
+ * Schroedinger's equation w.r.t. each control parameter -- the reference's exactness cross-check of the
+ * discrete adjoint (test/GradientTests/compare_gradients.jl:47-66).  One unforced solve, then P forced solves
+ * with zero initial state batched on the device (their forcing is formed on the fly from the resident
+ * history and the control basis table; no [2N, m, 1+nsteps, nic] forcing array per parameter exists).
+ *   pcof [P] (one control vector), target [2N, nic], grad [P]. */
+int qgd_eval_grad_forced(qgd_handle_t *h, const double *pcof, const double *target, int32_t order,
+                         double *grad);
+
 /* discrete_adjoint! (src/eval_grad_discrete_adjoint.jl:107-160), cost_type = :Infidelity.
  *   target      [2N, nic] real-stacked vcat(real, imag) of the complex gate (what
  *               complex_to_real produces at :126); ALL nic columns even when sharded

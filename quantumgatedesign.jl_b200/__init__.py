@@ -16,5 +16,5 @@ from .problem import (DiagonalHamiltonianPreconditioner, DispersiveProblem, Iden
 from . import backend
 from . import distributed
 from .api import (discrete_adjoint, discrete_adjoint_, discrete_adjoint_batch, eval_forward, eval_forward_,
-                  guard_penalty_real, infidelity, infidelity_real)
+                  eval_grad_forced, guard_penalty_real, infidelity, infidelity_real)
 from .backend import Handle, QGDError, get_handle, measure_fp64_peak

@@ -24,14 +24,13 @@ def _check_order(order):
 def eval_forward_(uv_history, prob, controls, pcof, order=2, saveEveryNsteps=1, forcing=None, device=-1):
     """eval_forward!(uv_history, prob, controls, pcof; order, saveEveryNsteps, forcing)."""
     _check_order(order)
-    if forcing is not None:
-        raise NotImplementedError("forced forward solves (eval_grad_forced) are not on the GPU path yet; see DESIGN.md")
     m = order // 2
     nsave = prob.nsteps // saveEveryNsteps
     shape = (prob.real_system_size, 1 + m, 1 + nsave, prob.N_initial_conditions)
     assert uv_history.shape == shape, f"uv_history must have shape {shape}"  # @assert of :43
     h = get_handle(prob, controls, device)
-    out = h.eval_forward(pcof, order=order, save_every=saveEveryNsteps, want_history=True, want_iters=False)
+    out = h.eval_forward(pcof, order=order, save_every=saveEveryNsteps, want_history=True, want_iters=False,
+                         forcing=forcing)
     uv_history[...] = out["history"][..., 0]
     return None
 
@@ -80,6 +79,16 @@ def discrete_adjoint(prob, controls, pcof, target, order=2, cost_type="Infidelit
     grad = np.zeros(len(pcof))
     return discrete_adjoint_(grad, None, None, None, prob, controls, pcof, target, order=order, cost_type=cost_type,
                              device=device)
+
+
+def eval_grad_forced(prob, controls, pcof, target, order=2, cost_type="Infidelity", device=-1):
+    """eval_grad_forced(prob, controls, pcof, target; order, cost_type) (src/eval_grad_forced.jl:18-26): the gradient
+    from one forced forward solve per control parameter -- the reference's exactness check of the adjoint."""
+    _check_order(order)
+    if cost_type not in ("Infidelity", ":Infidelity"):
+        raise ValueError(f"Invalid cost type: {cost_type} (only :Infidelity is on the GPU path)")
+    h = get_handle(prob, controls, device)
+    return h.eval_grad_forced(pcof, complex_to_real(target), order=order)
 
 
 def discrete_adjoint_batch(prob, controls, pcofs, target, order=2, device=-1, want_iters=False):

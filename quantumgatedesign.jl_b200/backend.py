@@ -25,6 +25,7 @@ EXPORTS = [
     "qgd_set_gmres_tolerances", "qgd_set_column_shard", "qgd_eval_forward", "qgd_discrete_adjoint",
     "qgd_discrete_adjoint_device", "qgd_adjoint_phase1", "qgd_adjoint_phase2", "qgd_infidelity_real",
     "qgd_eval_controls", "qgd_compute_derivatives", "qgd_get_stats", "qgd_measure_fp64_peak",
+    "qgd_eval_forward_forced", "qgd_eval_grad_forced",
 ]
 
 
@@ -74,6 +75,9 @@ def lib():
                                               C.c_int32]
         L.qgd_get_stats.argtypes = [C.c_void_p, C.POINTER(_abi.qgd_stats_t)]
         L.qgd_measure_fp64_peak.argtypes = [C.c_int, c_double_p]
+        L.qgd_eval_forward_forced.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int32, C.c_int64, c_double_p,
+                                              c_double_p, c_double_p, c_int64_p]
+        L.qgd_eval_grad_forced.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p]
         _LIB = L
     return _LIB
 
@@ -145,15 +149,40 @@ class Handle:
             raise ValueError(f"pcof has {pc.shape[0]} coefficients, the controls need {P}")
         return np.asfortranarray(pc)
 
-    def eval_forward(self, pcof, order=2, save_every=1, want_history=True, want_iters=True):
+    def eval_forward(self, pcof, order=2, save_every=1, want_history=True, want_iters=True, forcing=None):
+        """forcing: [2N, m, 1+nsteps, ncol(, B)] as eval_forward!(...; forcing) takes it, or None."""
         pc = self._pcof(pcof, self.P)
         B, m = pc.shape[1], order // 2
         nslots = 1 + self.nsteps // save_every
         hist = np.zeros((self.N2, 1 + m, nslots, self.ncol, B), order="F") if want_history else None
         final = np.zeros((self.N2, self.ncol, B), order="F")
         iters = np.zeros((self.nsteps, self.ncol, B), dtype=np.int64, order="F") if want_iters else None
-        _check(lib().qgd_eval_forward(self._h, _dp(pc), B, int(order), int(save_every), _dp(hist), _dp(final), _ip(iters)))
+        if forcing is None:
+            _check(lib().qgd_eval_forward(self._h, _dp(pc), B, int(order), int(save_every), _dp(hist), _dp(final),
+                                          _ip(iters)))
+        else:
+            f = np.asarray(forcing, dtype=np.float64)
+            if f.ndim == 4:
+                f = f[..., None]
+            shape = (self.N2, m, self.nsteps + 1, self.ncol, B)
+            if f.shape != shape:
+                raise ValueError(f"forcing must have shape {shape[:4]} (+ batch), got {f.shape}")
+            f = np.asfortranarray(f)
+            _check(lib().qgd_eval_forward_forced(self._h, _dp(pc), B, int(order), int(save_every), _dp(f), _dp(hist),
+                                                 _dp(final), _ip(iters)))
         return dict(history=hist, final_state=final, iters=iters)
+
+    def eval_grad_forced(self, pcof, target_real, order=2):
+        """eval_grad_forced (src/eval_grad_forced.jl:18-195): P forced solves batched on the device."""
+        pc = np.ascontiguousarray(pcof, dtype=np.float64)
+        if pc.shape != (self.P,):
+            raise ValueError(f"pcof has shape {pc.shape}, the controls need ({self.P},)")
+        tgt = np.asfortranarray(target_real, dtype=np.float64)
+        if tgt.shape != (self.N2, self.nic):
+            raise ValueError(f"target must be the real-stacked [2N, nic] = {(self.N2, self.nic)} array, got {tgt.shape}")
+        grad = np.zeros(self.P)
+        _check(lib().qgd_eval_grad_forced(self._h, _dp(pc), _dp(tgt), int(order), _dp(grad)))
+        return grad
 
     def discrete_adjoint(self, pcof, target_real, order=2, history_precomputed=False, want_history=False,
                          want_lambda=False, want_forcing=False, want_iters=False):

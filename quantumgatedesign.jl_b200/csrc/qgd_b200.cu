@@ -472,8 +472,10 @@ bool try_derivs_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a, dou
   QGD_FAST_SWITCH(d.m, launch_derivs_fast, h, d, a, h->fast_el, h->Nc, uv, ncols, cv, adjoint)
 }
 
-// forward sweep on device for B control vectors already in d_pcof
-void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t save_every, bool want_iters) {
+// forward sweep on device for B control vectors already in d_pcof; d_forcing: explicit forcing array
+// [2N][m][nsteps+1][ncol][B] on the device (generic kernels), or null
+void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t save_every, bool want_iters,
+                 const double* d_forcing = nullptr) {
   check_order(order);
   if (save_every < 1) throw QgdError(QGD_EINVAL, "saveEveryNsteps must be >= 1");
   const int m = order / 2, el = pick_el(h->N);
@@ -492,10 +494,38 @@ void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t 
   a.history = h->d_history.as<double>();
   a.final_state = h->d_final.as<double>();
   if (want_iters) { h->d_iters_f.reserve((size_t)h->nsteps * h->ncol * B * 4); a.iters = h->d_iters_f.as<int>(); }
+  a.forcing_in = d_forcing;
   CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
-  if (!try_forward_fast(h, d, a)) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
+  if (d_forcing || !try_forward_fast(h, d, a)) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
   CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
-  h->hist_B = B; h->hist_order = order; h->hist_nsteps = h->nsteps; h->hist_save = save_every; h->hist_valid = true;
+  h->hist_B = B; h->hist_order = order; h->hist_nsteps = h->nsteps; h->hist_save = save_every; h->hist_valid = d_forcing == nullptr;
+}
+
+// eval_grad_forced on the device: the unforced history of ONE control vector is resident (run_forward, save_every 1);
+// P forced forward solves with zero initial state -- one per control parameter, batched as P x ncol items -- form
+// their forcing on the fly from that history and the control basis table.  Leaves d psi_N / d theta in d_scratch
+// [2N][ncol][P] and the guard-penalty derivative partials in d_guardcol [ncol][P].
+void run_forced_gradient_solves(qgd_handle* h, int order) {
+  const int m = order / 2, el = pick_el(h->N), P = h->P;
+  QgdDevProb d = make_devprob(h, order);
+  SweepArgs a{};
+  a.B = P; a.save_every = 1; a.nslots = 1 + (int)h->nsteps;
+  a.cvals = h->d_cvals.as<double>();
+  a.history = nullptr;
+  h->d_scratch.reserve((size_t)h->N2 * h->ncol * P * 8);
+  a.final_state = h->d_scratch.as<double>();
+  h->d_guardcol.reserve((size_t)h->ncol * P * 8);
+  a.guardcol = h->d_guardcol.as<double>();
+  a.base_history = h->d_history.as<double>();
+  std::vector<int> top((size_t)P);
+  for (int k = 0; k < h->Nc; ++k)
+    for (int t = 0; t < h->ctrls[k].ncoeff; ++t) top[(size_t)h->ctrls[k].offset + t] = k + 1;  // blob operator 0 is the drift
+  h->d_theta_op.reserve((size_t)P * 4);
+  CUDA_CHECK(cudaMemcpyAsync(h->d_theta_op.p, top.data(), (size_t)P * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));  // `top` is a local
+  a.theta_op = h->d_theta_op.as<int>();
+  (void)m;
+  QGD_DISPATCH_EL(el, launch_forward, h, d, a);
 }
 
 // guard partials + (optionally) forcing array from the device-resident history
@@ -615,7 +645,8 @@ int qgd_destroy(qgd_handle_t* h) {
   DevBuf* bufs[] = {&h->d_blob, &h->d_minv[0], &h->d_minv[1], &h->d_u0, &h->d_v0, &h->d_ctrls, &h->d_aux, &h->d_table, &h->d_pcof,
                     &h->d_cvals, &h->d_history, &h->d_final, &h->d_final_all, &h->d_terminal, &h->d_lambda0, &h->d_lamhist,
                     &h->d_gradcol, &h->d_grad, &h->d_guardcol, &h->d_guard, &h->d_infid, &h->d_iters_f, &h->d_iters_a,
-                    &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch, &h->d_counter, &h->d_progress, &h->d_carry};
+                    &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch, &h->d_counter, &h->d_progress, &h->d_carry,
+                    &h->d_theta_op};
   for (DevBuf* b : bufs) b->release();
   if (h->l2_carved) cudaCtxResetPersistingL2Cache();  // hand the persisting L2 lines of the workspace window back
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -652,6 +683,71 @@ int qgd_eval_forward(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32
     if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
     iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
+    finish_timing(h, true, false);
+  });
+}
+
+int qgd_eval_forward_forced(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32_t order, int64_t save_every,
+                            const double* forcing, double* history, double* final_state, int64_t* gmres_iters) {
+  return guarded([&]() {
+    require(h && pcof && forcing && n_batch >= 1, "bad arguments");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    const int B = (int)n_batch, m = order / 2;
+    check_order(order);
+    h->d_pcof.reserve((size_t)std::max(h->P, 1) * B * 8);
+    h2d(h, h->d_pcof.p, pcof, (size_t)h->P * B * 8);
+    const size_t fbytes = (size_t)h->N2 * m * (h->nsteps + 1) * h->ncol * B * 8;
+    h->d_forcing.reserve(fbytes);
+    h2d(h, h->d_forcing.p, forcing, fbytes);
+    run_forward(h, h->d_pcof.as<double>(), B, order, save_every, gmres_iters != nullptr, h->d_forcing.as<double>());
+    const int nslots = 1 + (int)(h->nsteps / save_every);
+    if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * nslots * h->ncol * B * 8);
+    if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
+    finish_timing(h, true, false);
+  });
+}
+
+int qgd_eval_grad_forced(qgd_handle_t* h, const double* pcof, const double* target, int32_t order, double* grad) {
+  return guarded([&]() {
+    require(h && pcof && target && grad, "bad arguments");
+    if (h->ncol != h->nic) throw QgdError(QGD_EUNSUPPORTED, "qgd_eval_grad_forced needs all columns on one handle");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    const int P = h->P, N = h->N, N2 = h->N2, nic = h->nic;
+    h->d_pcof.reserve((size_t)std::max(P, 1) * 8);
+    h2d(h, h->d_pcof.p, pcof, (size_t)P * 8);
+    run_forward(h, h->d_pcof.as<double>(), 1, order, 1, false);  // history, d_final = psi_N (eval_grad_forced.jl:54-56)
+    if (P == 0) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); return; }
+    run_forced_gradient_solves(h, order);
+    dvec fs((size_t)N2 * nic), dfs((size_t)N2 * nic * P), gc((size_t)nic * P);
+    d2h(h, fs.data(), h->d_final.p, fs.size() * 8);
+    d2h(h, dfs.data(), h->d_scratch.p, dfs.size() * 8);
+    d2h(h, gc.data(), h->d_guardcol.p, gc.size() * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    // d infidelity / d theta = -(2 / N_ess^2) (<psi,R><dpsi,R> + <psi,T><dpsi,T>), T = [R_im; -R_re]  (:134-147)
+    auto dots = [&](const double* psi, double& dR, double& dT) {
+      dR = 0.0; dT = 0.0;
+      for (int c = 0; c < nic; ++c)
+        for (int r = 0; r < N; ++r) {
+          const double pu = psi[r + (size_t)N2 * c], pv = psi[N + r + (size_t)N2 * c];
+          const double Ru = target[r + (size_t)N2 * c], Rv = target[N + r + (size_t)N2 * c];
+          dR += pu * Ru + pv * Rv;
+          dT += pu * Rv - pv * Ru;
+        }
+    };
+    double dRf, dTf;
+    dots(fs.data(), dRf, dTf);
+    for (int t = 0; t < P; ++t) {
+      double dRp, dTp;
+      dots(dfs.data() + (size_t)N2 * nic * t, dRp, dTp);
+      double g = -(2.0 / ((double)h->Ness * h->Ness)) * (dRf * dRp + dTf * dTp);
+      for (int c = 0; c < nic; ++c) g += gc[(size_t)c + (size_t)nic * t];
+      grad[t] = g;
+    }
+    h->hist_valid = true;
     finish_timing(h, true, false);
   });
 }

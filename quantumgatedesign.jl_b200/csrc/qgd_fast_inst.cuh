@@ -76,9 +76,10 @@ void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, Sw
   a.warp_smem_doubles = L.warp_doubles;
 }
 
-// Launch a sweep kernel with an L2 access-policy window over the Krylov / Hessenberg workspace: those lines are
-// rewritten by every solve and should stay in the L2 while the state history streams through it (the history itself
-// is accessed with evict-first loads and stores).  QGD_L2_PERSIST=0 launches without the window.
+// Launch a sweep kernel, optionally (QGD_L2_PERSIST=1) with a persisting L2 access-policy window over the Krylov /
+// Hessenberg workspace.  Measured on B200 (profiles/r01_l2_policy.txt): the window TRIPLES the DRAM write traffic of a
+// sweep (7.8 GB instead of 2.3 GB at batch 148 x 110 steps) at equal run time, so it is off by default; what does help
+// is accessing the state history with evict-first loads and stores (-18 % writes, -50 % reads).
 template <class... KArgs, class... Args>
 void launch_sweep(qgd_handle* h, void (*kernel)(KArgs...), const FastCfg& L, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -89,7 +90,7 @@ void launch_sweep(qgd_handle* h, void (*kernel)(KArgs...), const FastCfg& L, Arg
   const char* env = getenv("QGD_L2_PERSIST");
   const size_t carve = (size_t)std::max(h->prop.persistingL2CacheMaxSize, 0);
   const size_t max_win = (size_t)std::max(h->prop.accessPolicyMaxWindowSize, 0);
-  if (!(env && atoi(env) == 0) && carve > 0 && max_win > 0 && h->d_V.cap > 0) {
+  if (env && atoi(env) == 1 && carve > 0 && max_win > 0 && h->d_V.cap > 0) {
     if (!h->l2_carved) {
       CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
       h->l2_carved = true;

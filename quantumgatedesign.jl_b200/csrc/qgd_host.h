@@ -66,7 +66,7 @@ struct qgd_handle {
   DevBuf d_table;
   // batch buffers
   DevBuf d_pcof, d_cvals, d_history, d_final, d_final_all, d_terminal, d_lambda0, d_lamhist, d_gradcol, d_grad, d_guardcol,
-      d_guard, d_infid, d_iters_f, d_iters_a, d_iters_t, d_target, d_forcing, d_V, d_H, d_scratch, d_counter, d_progress, d_carry;
+      d_guard, d_infid, d_iters_f, d_iters_a, d_iters_t, d_target, d_forcing, d_V, d_H, d_scratch, d_counter, d_progress, d_carry, d_theta_op;
   // state of the device-resident history
   int hist_B = 0, hist_order = 0;
   int64_t hist_nsteps = 0, hist_save = 0;

@@ -48,6 +48,11 @@ struct SweepArgs {
   double* terminal_out;    // [2N][nic][B]
   double* infidelity;      // [B]
   int* iters_term;         // [nic][B] or null
+  // forced forward solves (generic kernels only)
+  const double* forcing_in;    // eval_forward!(...; forcing): [2N][m][nsteps+1][ncol][B], or null
+  const double* base_history;  // eval_grad_forced: unforced history [2N][1+m][nsteps+1][ncol]; item b = control parameter b,
+                               // zero initial state, every item uses control vector 0, no history is written
+  const int* theta_op;         // eval_grad_forced: [P] blob index of the control operator of each parameter
 };
 
 // ---- TMA bulk copy of the operator blob into shared memory ------------------------------------------
@@ -122,30 +127,75 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_forward(const __grid
   FwdOp<EL> op;
   for (size_t item = (size_t)blockIdx.x * wpc + warp; item < items; item += (size_t)gridDim.x * wpc) {
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
-    const double* cvb = a.cvals + (size_t)b * (d.nsteps + 1) * cv_stride;
-    double* hist = a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b);
+    const bool gradf = a.base_history != nullptr;  // eval_grad_forced: item b is control parameter b
+    const bool forced = gradf || a.forcing_in != nullptr;
+    const double* cvb = a.cvals + (gradf ? (size_t)0 : (size_t)b * (d.nsteps + 1) * cv_stride);
+    double* hist = a.history ? a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
+    const double* fin = a.forcing_in ? a.forcing_in + (size_t)N2 * m * (d.nsteps + 1) * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
+    const double* hb = gradf ? a.base_history + slot_sz * (d.nsteps + 1) * (size_t)cl : nullptr;
+    const size_t tab_stride = (size_t)2 * (m + 1) * d.P;
+    auto forcing_at = [&](int n) {  // forcing of time level n
+      ForcingSrc F;
+      F.arr = fin ? fin + (size_t)N2 * m * n : nullptr;
+      F.hb = hb ? hb + slot_sz * n : nullptr;
+      F.tp = gradf ? d.table + tab_stride * n + b : nullptr;
+      F.tq = gradf ? F.tp + (size_t)(m + 1) * d.P : nullptr;
+      F.P = d.P; F.op = gradf ? a.theta_op[b] : 0;
+      return F;
+    };
+    // eval_grad_forced: d/dtheta of the guard penalty, dt/tf sum_n wt_n (<dpsi_n, W psi_n> + <psi_n, W dpsi_n>)
+    // (src/eval_grad_forced.jl:150-172)
+    double gpen = 0.0;
+    auto guard_cross = [&](const Vec<EL>& dx, int n) {
+      Vec<EL> w0, Wa, Wb;
+      vload(w0, hb + slot_sz * n, N, lane);
+      __syncwarp();
+      vstore(w0, c.wv, N, lane);
+      vstore(dx, c.wv + N2, N, lane);
+      __syncwarp();
+      guard_apply(c, c.wv, Wa);
+      guard_apply(c, c.wv + N2, Wb);
+      const double wt = (n == 0 || n == d.nsteps) ? 0.5 : 1.0;
+      gpen += wt * (vdot(dx, Wa) + vdot(w0, Wb));
+      __syncwarp();
+    };
     Vec<EL> x;
 #pragma unroll
     for (int e = 0; e < EL; ++e) {
       const int r = lane + 32 * e;
-      x.u[e] = r < N ? d.u0[r + (size_t)N * col] : 0.0;
-      x.v[e] = r < N ? d.v0[r + (size_t)N * col] : 0.0;
+      x.u[e] = (r < N && !gradf) ? d.u0[r + (size_t)N * col] : 0.0;
+      x.v[e] = (r < N && !gradf) ? d.v0[r + (size_t)N * col] : 0.0;
     }
     load_cv(c, cvb);
     for (int n = 0; n < d.nsteps; ++n) {
       Vec<EL> rhs, guess;
-      double* slot = (n % a.save_every == 0) ? hist + slot_sz * (n / a.save_every) : nullptr;
-      fwd_derivs<EL, true>(c, x, d.a_rhs, rhs, &guess, slot);  // explicit part at t_n
+      double* slot = (hist && n % a.save_every == 0) ? hist + slot_sz * (n / a.save_every) : nullptr;
+      if (gradf) guard_cross(x, n);
+      if (forced) {
+        const ForcingSrc F = forcing_at(n);
+        fwd_derivs<EL, true>(c, x, d.a_rhs, rhs, &guess, slot, &F);  // explicit part at t_n
+      } else {
+        fwd_derivs<EL, true>(c, x, d.a_rhs, rhs, &guess, slot);
+      }
       load_cv(c, cvb + (size_t)(n + 1) * cv_stride);            // implicit part uses t_{n+1}
+      if (forced) {  // the forcing of t_{n+1} is explicit: its implicit-side combination moves to the right-hand side
+        const ForcingSrc F1 = forcing_at(n + 1);  // (forward_evolution.jl:196-206)
+        Vec<EL> zero, fh;
+        vzero(zero);
+        fwd_derivs<EL, false>(c, zero, d.a_lhs, fh, nullptr, nullptr, &F1);
+        vaxpy(rhs, -1.0, fh);
+      }
       x = guess;
       const int it = gmres_warp<EL>(c, op, x, rhs, d.abstol, -1.0, N2, N2, 0);
       if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
     }
-    {  // Taylor columns at the final time (forward_evolution.jl:232-242)
+    {  // Taylor columns at the final time, WITHOUT forcing as in the reference (forward_evolution.jl:232-242)
       Vec<EL> dummy, guess;
-      double* slot = (d.nsteps % a.save_every == 0) ? hist + slot_sz * (d.nsteps / a.save_every) : nullptr;
+      double* slot = (hist && d.nsteps % a.save_every == 0) ? hist + slot_sz * (d.nsteps / a.save_every) : nullptr;
+      if (gradf) guard_cross(x, d.nsteps);
       fwd_derivs<EL, true>(c, x, d.a_rhs, dummy, &guess, slot);
       vstore(x, a.final_state + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b), N, lane);
+      if (gradf && lane == 0) a.guardcol[(size_t)cl + (size_t)d.ncol * b] = gpen * (d.dt / d.tf);
     }
   }
 }

@@ -162,11 +162,24 @@ __device__ __forceinline__ void load_cv(const WarpCtx& c, const double* src /*gl
   __syncwarp();
 }
 
-// out = sum_j alpha_j w_j with w_0 = x and w_{j+1} = (1/(j+1)) sum_{i<=j} A_{j-i} w_i.
+// Forcing of the Taylor recursion at one time level (compute_derivatives!(...; forcing_matrix), reference
+// src/hermite.jl:91-95): either an explicit array (eval_forward!(...; forcing), src/forward_evolution.jl:118-129) or
+// the forcing of eval_grad_forced (src/eval_grad_forced.jl:82-131) formed on the fly,
+//   f_j = sum_{i<=j} d/dtheta [p^(j-i)/(j-i)!] [K w_i]-part + d/dtheta [q^(j-i)/(j-i)!] [S w_i]-part,
+// from the Taylor columns w_i of the unforced solution (hb, global memory) and the control basis table.
+struct ForcingSrc {
+  const double* arr;  // [2N][m] explicit forcing of this time level, or null
+  const double* hb;   // [2N][1+m] unforced Taylor columns of this time level, or null
+  const double* tp;   // tp[r * P] = d/dtheta p^(r)/r! at this time level; tq likewise
+  const double* tq;
+  int P, op;          // op: blob index of the control operator theta belongs to
+};
+
+// out = sum_j alpha_j w_j with w_0 = x and w_{j+1} = (1/(j+1)) (sum_{i<=j} A_{j-i} w_i + f_j).
 // STEP: also guess = sum_j a_tay_j w_j and (if hist != nullptr) hist[:, j] = w_j (history slot).
 template <int EL, bool STEP>
 __device__ void fwd_derivs(const WarpCtx& c, const Vec<EL>& x, const double* alpha, Vec<EL>& out, Vec<EL>* guess,
-                           double* hist) {
+                           double* hist, const ForcingSrc* F = nullptr) {
   const QgdDevProb& d = *c.d;
   const int N = d.N, N2 = d.N2, m = d.m, nops = d.lay.n_ops, lane = c.lane;
   __syncwarp();
@@ -201,6 +214,21 @@ __device__ void fwd_derivs(const WarpCtx& c, const Vec<EL>& x, const double* alp
             au = fma(cs, zSu, fma(ck, zKv, au));
             av = fma(cs, zSv, fma(-ck, zKu, av));
           }
+        }
+        if (F) {
+          double fu = 0.0, fv = 0.0;
+          if (F->arr) { fu = F->arr[r + (size_t)N2 * j]; fv = F->arr[N + r + (size_t)N2 * j]; }
+          if (F->hb) {
+            for (int i = j; i >= 0; --i) {
+              const int dd = j - i;
+              double zKu, zKv, zSu, zSv;
+              op_zsums(c, F->op, r, F->hb + (size_t)i * N2, zKu, zKv, zSu, zSv);
+              const double pv = F->tp[(size_t)dd * F->P], qv = F->tq[(size_t)dd * F->P];
+              fu = fma(pv, zKv, fma(qv, zSu, fu));
+              fv = fma(-pv, zKu, fma(qv, zSv, fv));
+            }
+          }
+          au += fu; av += fv;
         }
       }
       acc.u[e] = au * inv;

@@ -292,3 +292,38 @@ def test_high_order_convergence_on_gpu(q, order):
     print("order", order, "errors", errs, "halving rates", rates)
     assert len(rates) >= 2 and all(r > 4.0 for r in rates), (errs, rates)
     assert order - 1.2 < max(rates) < order + 0.8, (order, rates, errs)
+
+
+# ---- forced forward solves and eval_grad_forced --------------------------------------
+@pytest.mark.parametrize("name", ["cnot2", "cnot3_333", "dense_o10", "rand_grape"])
+def test_forced_forward_vs_oracle(q, O, name):
+    """eval_forward!(...; forcing) (src/forward_evolution.jl:118-129, 167-206): random forcing array, full history
+    and GMRES iteration counts vs the oracle."""
+    prob, controls, pcof, target, order = _cases(q)[name]
+    m = order // 2
+    rng = np.random.default_rng(5)
+    forcing = 1e-2 * rng.standard_normal((prob.real_system_size, m, prob.nsteps + 1, prob.N_initial_conditions))
+    forcing = np.asfortranarray(forcing)
+    h = q.Handle(prob, controls)
+    out = h.eval_forward(pcof, order=order, forcing=forcing)
+    ref_hist, ref_it = O.eval_forward(prob, controls, pcof, order=order, forcing=forcing)
+    assert rel(out["history"][..., 0], ref_hist) < RTOL
+    assert np.array_equal(out["iters"][:, :, 0], ref_it)
+    # the forcing really enters (the unforced history differs)
+    plain = h.eval_forward(pcof, order=order)
+    assert rel(plain["history"][..., 0], ref_hist) > 1e-6
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["cnot2", "cnot3_333", "rabi_carrier", "rand_grape"])
+def test_eval_grad_forced_vs_oracle_and_adjoint(q, O, name):
+    """eval_grad_forced (src/eval_grad_forced.jl:18-195) batched over the control parameters on the device: equal to the
+    oracle's forced gradient (1e-10) and to the discrete-adjoint gradient of the same GPU path -- the reference's own
+    exactness check (test/GradientTests/compare_gradients.jl:47-66)."""
+    prob, controls, pcof, target, order = _cases(q)[name]
+    gf = q.eval_grad_forced(prob, controls, pcof, target, order=order)
+    ref = O.eval_grad_forced(prob, controls, pcof, target, order=order)
+    assert rel(gf, ref) < RTOL
+    ga = q.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert rel(ga, gf) < 1e-9
+    q.backend.clear_handles()
