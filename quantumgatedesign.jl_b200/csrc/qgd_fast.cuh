@@ -873,6 +873,131 @@ __device__ __forceinline__ void qr_solve_fast(const CTX& c, int width, double be
   __syncwarp();
 }
 
+// ---- the same least-squares solve with a short dependent chain (QGD_QR_LEAN, the default) -----------------
+// Profile of the ring version (profiles/r01_ncu_source_v8_fwd.txt): ~200 instructions and ~900 cycles per rotation,
+// ~500 per back-substitution step -- 18 % of a sweep.  Here the rotation loop is split into phases of 32 rotations so
+// that the pivot owner's register is indexed statically, the rows of H two and three rotations ahead are prefetched
+// straight into registers, the special cases of givensAlgorithm fold into the sign of one reciprocal square root
+// (1 / r_ii IS that reciprocal square root: no division), and lane 0's stores are predicated, not branched.
+#ifndef QGD_QR_LEAN
+#define QGD_QR_LEAN 1
+#endif
+template <int S0, int CH>
+__device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* const (&colp)[CH], const double* sub, double* dinv,
+                                                  double* g, double& gcur, int width, int nsl, int lane) {
+  const int i0 = 32 * S0;
+  if (i0 >= width) return;
+  const int iend = min(width, i0 + 32);
+  double loA[CH], loB[CH];
+  auto fetch = [&](double (&lo)[CH], int r) {  // row r of the owned columns j = lane + 32 s >= r - 1
+#pragma unroll
+    for (int s = S0; s < CH; ++s) {
+      const int j = lane + 32 * s;
+      lo[s] = (s < nsl && j < width && r <= j + 1) ? __ldcg(colp[s] + r) : 0.0;
+    }
+  };
+  auto rotate = [&](int i, const double (&lo)[CH]) {
+    const double a = __shfl_sync(FULL_MASK, top[S0], i & 31);
+    const double b = sub[i];
+    double rr = rsqrt(fma(a, a, b * b));
+    // LinearAlgebra.givensAlgorithm: r = +-sqrt(a^2 + b^2), negative only when |a| > |b| and a < 0
+    rr = (a < 0.0 && fabs(a) > fabs(b)) ? -rr : rr;
+    const double cs = a * rr, sn = b * rr;
+#pragma unroll
+    for (int s = S0; s < CH; ++s) {
+      const int j = lane + 32 * s;
+      if (s < nsl && j < width && j >= i) {
+        const double r = cs * top[s] + sn * lo[s];
+        top[s] = -sn * top[s] + cs * lo[s];
+        if (j > i) colp[s][i] = r;
+      }
+    }
+    if (lane == 0) { dinv[i] = rr; g[i] = cs * gcur; }  // r_ii = cs a + sn b = 1 / rr
+    gcur = -sn * gcur;
+  };
+  fetch(loA, i0 + 1);
+  fetch(loB, i0 + 2);
+  for (int i = i0; i < iend; i += 2) {
+    rotate(i, loA);
+    fetch(loA, i + 3);
+    if (i + 1 < iend) {
+      rotate(i + 1, loB);
+      fetch(loB, i + 4);
+    }
+  }
+}
+
+// back substitution R y = g for the rows [32 S0, 32 S0 + 32) of the pivot: right-hand side rows i = lane + 32 q in
+// registers, column j of R (contiguous in L2) prefetched two steps ahead
+template <int S0, int CH>
+__device__ __forceinline__ void qr_backsub_phase(double (&gi)[CH], const double* Rg, const double* dinv, int width, int lane) {
+  const int j_lo = 32 * S0;
+  if (j_lo >= width) return;
+  const int j_hi = min(width, j_lo + 32) - 1;
+  double cA[CH], cB[CH];
+  auto fetch = [&](double (&col)[CH], int j) {  // rows i < j of column j
+    const double* src = Rg + hoff(max(j, 0));
+#pragma unroll
+    for (int q = 0; q <= S0; ++q) {
+      const int i = lane + 32 * q;
+      col[q] = (j >= 0 && i < j) ? __ldcg(src + i) : 0.0;
+    }
+  };
+  auto step = [&](int j, const double (&col)[CH]) {
+    const double yj = __shfl_sync(FULL_MASK, gi[S0], j & 31) * dinv[j];
+#pragma unroll
+    for (int q = 0; q <= S0; ++q) {
+      const int i = lane + 32 * q;
+      gi[q] = i < j ? fma(-yj, col[q], gi[q]) : (i == j ? yj : gi[q]);
+    }
+  };
+  fetch(cA, j_hi);
+  fetch(cB, j_hi - 1);
+  for (int j = j_hi; j >= j_lo; j -= 2) {
+    step(j, cA);
+    fetch(cA, j - 2);
+    if (j - 1 >= j_lo) {
+      step(j - 1, cB);
+      fetch(cB, j - 3);
+    }
+  }
+}
+
+template <class CTX>
+__device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double beta) {
+  const int lane = c.lane;
+  constexpr int CH = 4;  // width <= restart <= 128
+  const int nsl = (width + 31) >> 5;
+  double* dinv = c.hcol;
+  __syncwarp();
+  double* colp[CH];
+  double top[CH];
+#pragma unroll
+  for (int s = 0; s < CH; ++s) {
+    const int j = lane + 32 * s;
+    colp[s] = c.Rg + hoff(j);
+    top[s] = j < width ? __ldcg(colp[s]) : 0.0;
+  }
+  double gcur = beta;
+  qr_rotation_phase<0, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
+  qr_rotation_phase<1, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
+  qr_rotation_phase<2, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
+  qr_rotation_phase<3, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
+  __threadfence_block();
+  __syncwarp();  // R (L2), dinv and g (shared memory) of all lanes are visible
+  double gi[CH];
+#pragma unroll
+  for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; gi[q] = i < width ? c.g[i] : 0.0; }
+  qr_backsub_phase<3, CH>(gi, c.Rg, dinv, width, lane);
+  qr_backsub_phase<2, CH>(gi, c.Rg, dinv, width, lane);
+  qr_backsub_phase<1, CH>(gi, c.Rg, dinv, width, lane);
+  qr_backsub_phase<0, CH>(gi, c.Rg, dinv, width, lane);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; if (i < width) c.g[i] = gi[q]; }
+  __syncwarp();
+}
+
 // GMRES with the blocked orthogonalisation; same interface and iteration semantics as gmres_fast_strict.
 template <int EL, int NC, int VARIANT, class OP>
 __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
@@ -935,7 +1060,8 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
     __syncwarp();
     if (k == restart + 1 || conv) {
       const int width = k - 1;
-      qr_solve_fast(c, width, res_beta);
+      if constexpr (QGD_QR_LEAN) qr_solve_lean(c, width, res_beta);
+      else qr_solve_fast(c, width, res_beta);
       Vec<EL> vi;
       basis_load<EL>(c, 0, vi);
       for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 0..width-1] y
