@@ -40,7 +40,7 @@ def parse():
                     help="control vectors per GPU per step")
     ap.add_argument("--nsteps", type=int, default=550)
     ap.add_argument("--shard", default="pcof", choices=["pcof", "columns"])
-    ap.add_argument("--cpu-sample-steps", type=int, default=int(os.environ.get("QGD_CPU_SAMPLE_STEPS", "110")),
+    ap.add_argument("--cpu-sample-steps", type=int, default=int(os.environ.get("QGD_CPU_SAMPLE_STEPS", "550")),
                     help="time steps of the C2 problem the CPU baseline integrates per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -353,10 +353,14 @@ def run_b200(args):
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         tpe = min(prob.N_initial_conditions, cores)
-        v, dt, S = cpu_sample(q, args, 1, tpe)
-        cpu = {"value": v, "unit": UNIT, "cores": tpe, "kind": "port",
-               "sample": f"1 gradient evaluation of the first {S} of {args.nsteps} time steps of C2 ({dt:.1f} s), scaled; "
-                         "C++ restatement of the reference as written (Julia unavailable)"}
+        reps, tot, frac_done = 0, 0.0, 0.0
+        while reps < 2 or (tot < 10.0 and reps < 8):  # about 10-30 s of CPU work
+            v, dt, S = cpu_sample(q, args, 1, tpe)
+            reps += 1; tot += dt; frac_done += S / args.nsteps
+        cpu = {"value": frac_done / tot, "unit": UNIT, "cores": tpe, "kind": "port",
+               "sample": f"{reps} gradient evaluations of the first {S} of {args.nsteps} time steps of C2, one after the other "
+                         f"({tot:.1f} s), {tpe} threads (one per column, like Threads.@threads); C++ restatement of the "
+                         "reference as written (Julia unavailable)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

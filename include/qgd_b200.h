@@ -55,6 +55,9 @@ typedef struct qgd_matrix {
 #define QGD_CONTROL_GRAPE 1           /* GRAPEControl(N_amplitudes, tf)      grape_control.jl:18-26   */
 #define QGD_CONTROL_BSPLINE2 2        /* BSpline2Control(D1, tf)             bspline_control.jl:21-43 */
 #define QGD_CONTROL_FORTRAN_BSPLINE 3 /* FortranBSplineControl(degree, N_basis, tf) FortranBSpline.jl:16-61 */
+#define QGD_CONTROL_HOST_TABLE 4      /* any other AbstractControl (src/Controls/Control.jl:6-27: GeneralBSplineControl,
+                                       * HermiteControl, HermiteCarrierControl, bcarrier2 ...): the host evaluates the
+                                       * control protocol and passes tables (qgd_*_tables below); n_amplitudes = N_coeff */
 typedef struct qgd_control {
   int32_t type;          /* base control type, QGD_CONTROL_*                              */
   int32_t reserved;
@@ -148,6 +151,21 @@ int qgd_eval_forward_forced(qgd_handle_t *h, const double *pcof, int64_t n_batch
  *   pcof [P] (one control vector), target [2N, nic], grad [P]. */
 int qgd_eval_grad_forced(qgd_handle_t *h, const double *pcof, const double *target, int32_t order,
                          double *grad);
+
+/* Host-evaluated controls: the sweeps only consume p_k^(j)(t_n)/j!, q_k^(j)(t_n)/j! and, for the gradient,
+ * d/dtheta of the same (what fill_p_mat!/fill_q_mat!, src/Controls/Control.jl:99-149, and eval_grad_p_derivative! /
+ * eval_grad_q_derivative! return, divided by j!).  For control types the device kernels do not evaluate, or when any
+ * control is QGD_CONTROL_HOST_TABLE, the caller fills these tables with the reference's own control code:
+ *   cvals [Nc, 1+m, 2, 1+nsteps, n_batch]   cvals[k, j, 0, n, b] = p_k^(j)(t_n)/j!, [.., 1, ..] = q_k^(j)(t_n)/j!
+ *   table [P,  1+m, 2, 1+nsteps]            table[theta, j, 0, n] = d/dtheta p_k(theta)^(j)(t_n)/j!  (shared by the
+ *                                           batch: controls linear in pcof; nonlinear controls use n_batch = 1)
+ * (column-major, first index fastest, t_n = n tf/nsteps).  Outputs as qgd_eval_forward / qgd_discrete_adjoint. */
+int qgd_eval_forward_tables(qgd_handle_t *h, int64_t n_batch, int32_t order, int64_t save_every,
+                            const double *cvals, double *history, double *final_state,
+                            int64_t *gmres_iters);
+int qgd_discrete_adjoint_tables(qgd_handle_t *h, int64_t n_batch, int32_t order, const double *cvals,
+                                const double *table, const double *target, double *grad,
+                                double *infidelity, double *guard_penalty);
 
 /* discrete_adjoint! (src/eval_grad_discrete_adjoint.jl:107-160), cost_type = :Infidelity.
  *   target      [2N, nic] real-stacked vcat(real, imag) of the complex gate (what

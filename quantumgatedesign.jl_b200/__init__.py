@@ -8,7 +8,8 @@ eval_forward, discrete_adjoint, infidelity ...) over the C ABI of csrc/libqgd_b2
 from . import _abi
 from . import configs
 from .controls import (AbstractControl, BSpline2Control, CarrierControl, FortranBSplineControl, GRAPEControl,
-                       as_control_list, control_slices, get_number_of_control_parameters)
+                       HostEvaluatedControl, SinCosControl, as_control_list, build_control_tables, control_slices,
+                       get_number_of_control_parameters, has_host_controls)
 from .problem import (DiagonalHamiltonianPreconditioner, DispersiveProblem, IdentityPreconditioner, LUPreconditioner,
                       SchrodingerProb, complex_to_real, construct_rabi_prob, construct_rand_prob, control_ops,
                       create_gate, create_initial_conditions, guard_projector, lowering_operators_system,

@@ -25,6 +25,7 @@ QGD_MAT_CSC = 1
 QGD_CONTROL_GRAPE = 1
 QGD_CONTROL_BSPLINE2 = 2
 QGD_CONTROL_FORTRAN_BSPLINE = 3
+QGD_CONTROL_HOST_TABLE = 4
 QGD_PRECOND_IDENTITY = 0
 QGD_PRECOND_LU = 1
 QGD_PRECOND_DIAGONAL = 2

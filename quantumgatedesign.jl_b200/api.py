@@ -13,6 +13,7 @@ from __future__ import annotations
 import numpy as np
 
 from .backend import get_handle
+from .controls import build_control_tables, has_host_controls
 from .problem import complex_to_real, real_to_complex
 
 
@@ -29,8 +30,14 @@ def eval_forward_(uv_history, prob, controls, pcof, order=2, saveEveryNsteps=1, 
     shape = (prob.real_system_size, 1 + m, 1 + nsave, prob.N_initial_conditions)
     assert uv_history.shape == shape, f"uv_history must have shape {shape}"  # @assert of :43
     h = get_handle(prob, controls, device)
-    out = h.eval_forward(pcof, order=order, save_every=saveEveryNsteps, want_history=True, want_iters=False,
-                         forcing=forcing)
+    if has_host_controls(controls):  # families the device does not evaluate: host-filled tables (qgd_eval_forward_tables)
+        if forcing is not None:
+            raise NotImplementedError("forcing with host-evaluated controls")
+        cvals, _ = build_control_tables(controls, pcof, prob.tf, prob.nsteps, m)
+        out = h.eval_forward_tables(cvals, order=order, save_every=saveEveryNsteps, want_history=True, want_iters=False)
+    else:
+        out = h.eval_forward(pcof, order=order, save_every=saveEveryNsteps, want_history=True, want_iters=False,
+                             forcing=forcing)
     uv_history[...] = out["history"][..., 0]
     return None
 
@@ -58,6 +65,13 @@ def discrete_adjoint_(grad, history, lambda_history, adjoint_forcing, prob, cont
                          "src/eval_grad_discrete_adjoint.jl:80)")
     tgt = complex_to_real(target)
     h = get_handle(prob, controls, device)
+    if has_host_controls(controls):
+        if history is not None or lambda_history is not None or adjoint_forcing is not None or history_precomputed:
+            raise NotImplementedError("host-evaluated controls return the gradient, infidelity and guard penalty only")
+        cvals, table = build_control_tables(controls, pcof, prob.tf, prob.nsteps, order // 2)
+        out = h.discrete_adjoint_tables(cvals, table, tgt, order=order)
+        grad[...] = out["grad"][:, 0]
+        return (grad, out) if return_info else grad
     out = h.discrete_adjoint(pcof, tgt, order=order, history_precomputed=history_precomputed,
                              want_history=history is not None and not history_precomputed,
                              want_lambda=lambda_history is not None, want_forcing=adjoint_forcing is not None,
@@ -111,7 +125,11 @@ def infidelity_real(psi, target, N_ess):
 def infidelity(prob, controls, pcof, target, order=2, device=-1):
     """src/infidelity.jl:34-47: forward solve on the GPU, then the infidelity of the final state."""
     h = get_handle(prob, controls, device)
-    out = h.eval_forward(pcof, order=order, want_history=False, want_iters=False)
+    if has_host_controls(controls):
+        cvals, _ = build_control_tables(controls, pcof, prob.tf, prob.nsteps, order // 2)
+        out = h.eval_forward_tables(cvals, order=order, want_history=False, want_iters=False)
+    else:
+        out = h.eval_forward(pcof, order=order, want_history=False, want_iters=False)
     return infidelity_real(out["final_state"][:, :, 0], complex_to_real(target), prob.N_ess_levels)
 
 

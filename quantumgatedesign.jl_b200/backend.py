@@ -25,7 +25,7 @@ EXPORTS = [
     "qgd_set_gmres_tolerances", "qgd_set_column_shard", "qgd_eval_forward", "qgd_discrete_adjoint",
     "qgd_discrete_adjoint_device", "qgd_adjoint_phase1", "qgd_adjoint_phase2", "qgd_infidelity_real",
     "qgd_eval_controls", "qgd_compute_derivatives", "qgd_get_stats", "qgd_measure_fp64_peak",
-    "qgd_eval_forward_forced", "qgd_eval_grad_forced",
+    "qgd_eval_forward_forced", "qgd_eval_grad_forced", "qgd_eval_forward_tables", "qgd_discrete_adjoint_tables",
 ]
 
 
@@ -78,6 +78,10 @@ def lib():
         L.qgd_eval_forward_forced.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int32, C.c_int64, c_double_p,
                                               c_double_p, c_double_p, c_int64_p]
         L.qgd_eval_grad_forced.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p]
+        L.qgd_eval_forward_tables.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, c_double_p, c_double_p,
+                                              c_double_p, c_int64_p]
+        L.qgd_discrete_adjoint_tables.argtypes = [C.c_void_p, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                                  c_double_p, c_double_p, c_double_p]
         _LIB = L
     return _LIB
 
@@ -171,6 +175,37 @@ class Handle:
             _check(lib().qgd_eval_forward_forced(self._h, _dp(pc), B, int(order), int(save_every), _dp(f), _dp(hist),
                                                  _dp(final), _ip(iters)))
         return dict(history=hist, final_state=final, iters=iters)
+
+    # -- host-evaluated controls (QGD_CONTROL_HOST_TABLE): tables instead of pcof
+    def eval_forward_tables(self, cvals, order=2, save_every=1, want_history=True, want_iters=True):
+        cv = np.asfortranarray(cvals, dtype=np.float64)
+        m = order // 2
+        B = cv.shape[4]
+        assert cv.shape == (self.Nc, m + 1, 2, self.nsteps + 1, B), cv.shape
+        nslots = 1 + self.nsteps // save_every
+        hist = np.zeros((self.N2, 1 + m, nslots, self.ncol, B), order="F") if want_history else None
+        final = np.zeros((self.N2, self.ncol, B), order="F")
+        iters = np.zeros((self.nsteps, self.ncol, B), dtype=np.int64, order="F") if want_iters else None
+        _check(lib().qgd_eval_forward_tables(self._h, B, int(order), int(save_every), _dp(cv), _dp(hist), _dp(final),
+                                             _ip(iters)))
+        return dict(history=hist, final_state=final, iters=iters)
+
+    def discrete_adjoint_tables(self, cvals, table, target_real, order=2):
+        cv = np.asfortranarray(cvals, dtype=np.float64)
+        tb = np.asfortranarray(table, dtype=np.float64)
+        m = order // 2
+        B = cv.shape[4]
+        assert cv.shape == (self.Nc, m + 1, 2, self.nsteps + 1, B), cv.shape
+        assert tb.shape == (self.P, m + 1, 2, self.nsteps + 1), tb.shape
+        tgt = np.asfortranarray(target_real, dtype=np.float64)
+        if tgt.shape != (self.N2, self.nic):
+            raise ValueError(f"target must be the real-stacked [2N, nic] = {(self.N2, self.nic)} array, got {tgt.shape}")
+        grad = np.zeros((self.P, B), order="F")
+        infid = np.zeros(B)
+        guard = np.zeros(B)
+        _check(lib().qgd_discrete_adjoint_tables(self._h, B, int(order), _dp(cv), _dp(tb), _dp(tgt), _dp(grad), _dp(infid),
+                                                 _dp(guard)))
+        return dict(grad=grad, infidelity=infid, guard_penalty=guard)
 
     def eval_grad_forced(self, pcof, target_real, order=2):
         """eval_grad_forced (src/eval_grad_forced.jl:18-195): P forced solves batched on the device."""

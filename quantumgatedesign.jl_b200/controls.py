@@ -110,6 +110,83 @@ class CarrierControl(AbstractControl):
         return f"CarrierControl({self.base_control!r}, {self.carrier_frequencies.tolist()})"
 
 
+class HostEvaluatedControl(AbstractControl):
+    """Any other AbstractControl (src/Controls/Control.jl:6-27 -- GeneralBSplineControl, the Hermite controls,
+    bcarrier2, user-defined ones): the device kernels do not know the family, so the HOST evaluates the control
+    protocol and the sweeps consume tables (include/qgd_b200.h, qgd_*_tables).
+
+    `derivatives(t, pcof_local, nderiv)` returns the un-scaled time derivatives of orders 0..nderiv-1,
+    `(p[nderiv], q[nderiv], grad_p[nderiv, N_coeff], grad_q[nderiv, N_coeff])` -- what eval_p_derivative /
+    eval_q_derivative / eval_grad_p_derivative! / eval_grad_q_derivative! return in the reference."""
+
+    def __init__(self, N_coeff, tf, derivatives, linear=True):
+        self.N_coeff = int(N_coeff)
+        self.tf = float(tf)
+        self.derivatives = derivatives
+        self.linear = bool(linear)  # p, q linear in pcof: the gradient table is shared by a batch of control vectors
+
+    def __repr__(self):
+        return f"HostEvaluatedControl(N_coeff={self.N_coeff}, tf={self.tf})"
+
+
+class SinCosControl(HostEvaluatedControl):
+    """SinCosControl(tf; frequency) (src/Controls/sincos_control.jl:1-27): p = sin(w t) pcof[1], q = cos(w t) pcof[2];
+    a family the device control kernels do not evaluate, served through the host-table path."""
+
+    def __init__(self, tf, frequency=1.0):
+        self.frequency = float(frequency)
+        w = self.frequency
+
+        def derivs(t, pc, nderiv):
+            j = np.arange(nderiv)
+            s = w ** j * np.sin(w * t + j * np.pi / 2)
+            c = w ** j * np.cos(w * t + j * np.pi / 2)
+            gp = np.zeros((nderiv, 2)); gq = np.zeros((nderiv, 2))
+            gp[:, 0] = s; gq[:, 1] = c
+            return s * pc[0], c * pc[1], gp, gq
+
+        super().__init__(2, tf, derivs, linear=True)
+
+
+def has_host_controls(controls) -> bool:
+    return any(isinstance(c, HostEvaluatedControl) for c in as_control_list(controls))
+
+
+def build_control_tables(controls, pcofs, tf, nsteps, m):
+    """Tables of the qgd_*_tables entry points for host-evaluated controls (t_n = n tf / nsteps):
+    cvals [Nc, 1+m, 2, 1+nsteps, B] = p_k^(j)/j!, q_k^(j)/j!;  table [P, 1+m, 2, 1+nsteps] = d/dtheta of the same."""
+    from math import factorial
+
+    cl = as_control_list(controls)
+    for c in cl:
+        if not isinstance(c, HostEvaluatedControl):
+            raise TypeError("host control tables: every control of the collection must be a HostEvaluatedControl "
+                            f"(got {type(c).__name__}; the device-evaluated families have no host evaluator here)")
+    pcofs = np.asarray(pcofs, dtype=np.float64)
+    if pcofs.ndim == 1:
+        pcofs = pcofs[:, None]
+    P, B = pcofs.shape
+    if B > 1 and not all(c.linear for c in cl):
+        raise ValueError("controls that are nonlinear in pcof need one call per control vector (the gradient table is shared)")
+    Nc, Nt = len(cl), nsteps + 1
+    cvals = np.zeros((Nc, m + 1, 2, Nt, B), order="F")
+    table = np.zeros((P, m + 1, 2, Nt), order="F")
+    inv_fact = np.array([1.0 / factorial(j) for j in range(m + 1)])
+    sl = control_slices(cl)
+    for n in range(Nt):
+        t = n * tf / nsteps
+        for k, c in enumerate(cl):
+            a, b = sl[k]
+            for ib in range(B):
+                pv, qv, gp, gq = c.derivatives(t, pcofs[a:b, ib], m + 1)
+                cvals[k, :, 0, n, ib] = np.asarray(pv) * inv_fact
+                cvals[k, :, 1, n, ib] = np.asarray(qv) * inv_fact
+                if ib == 0:
+                    table[a:b, :, 0, n] = (np.asarray(gp) * inv_fact[:, None]).T
+                    table[a:b, :, 1, n] = (np.asarray(gq) * inv_fact[:, None]).T
+    return cvals, table
+
+
 def as_control_list(controls) -> List[AbstractControl]:
     if isinstance(controls, AbstractControl):
         return [controls]
@@ -143,7 +220,12 @@ def control_descriptor(c: AbstractControl):
     else:
         d.n_carriers = 0
     d.tf = float(base.tf)
-    if isinstance(base, GRAPEControl):
+    if isinstance(base, HostEvaluatedControl):
+        if isinstance(c, CarrierControl):
+            raise TypeError("CarrierControl of a host-evaluated control: evaluate the carrier on the host as well")
+        d.type = _abi.QGD_CONTROL_HOST_TABLE
+        d.n_amplitudes = base.N_coeff
+    elif isinstance(base, GRAPEControl):
         d.type = _abi.QGD_CONTROL_GRAPE
         d.n_amplitudes = base.N_amplitudes
     elif isinstance(base, BSpline2Control):
@@ -155,7 +237,7 @@ def control_descriptor(c: AbstractControl):
         d.n_basis = base.N_basis_functions
     else:
         raise TypeError(
-            f"control type {type(base).__name__} is not on the B200 hot path "
-            "(GRAPE, BSpline2, FortranBSpline, Carrier are; see DESIGN.md 'out of scope')"
+            f"control type {type(base).__name__} is not evaluated on the device (GRAPE, BSpline2, FortranBSpline, "
+            "Carrier are): wrap it in HostEvaluatedControl to use the host-table path"
         )
     return d, keep

@@ -179,8 +179,13 @@ void validate_and_load(qgd_handle* h, const qgd_problem_t* p) {
       for (int i = 0; i < dc.order - 1; ++i) kn.push_back(0.0);
       for (int i = 0; i < dc.N_distinct; ++i) kn.push_back((double)i / (double)(dc.N_distinct - 1));
       for (int i = 0; i < dc.order - 1; ++i) kn.push_back(1.0);
+    } else if (c.type == QGD_CONTROL_HOST_TABLE) {
+      if (c.n_amplitudes < 0 || c.n_carriers > 0) throw QgdError(QGD_EINVAL, "host-table control: n_amplitudes = N_coeff >= 0, no carriers");
+      dc.base_ncoeff = dc.n_amp;
+      h->host_controls = true;
     } else {
-      throw QgdError(QGD_EUNSUPPORTED, "control type is not on the B200 hot path (GRAPE, BSpline2, FortranBSpline, Carrier)");
+      throw QgdError(QGD_EUNSUPPORTED, "control type is not evaluated on the device (GRAPE, BSpline2, FortranBSpline, Carrier are); "
+                                       "declare it QGD_CONTROL_HOST_TABLE and use the qgd_*_tables entry points");
     }
     if (dc.n_carriers > 0) h->ctrl_freqs[k].assign(c.carrier_freqs, c.carrier_freqs + dc.n_carriers);
     dc.ncoeff = dc.n_carriers > 0 ? dc.base_ncoeff * dc.n_carriers : dc.base_ncoeff;
@@ -390,6 +395,9 @@ void check_order(int order) {
 
 // control basis table for t_n = n dt, n = 0..nsteps (cached per (nsteps, m))
 void ensure_table(qgd_handle* h, int m) {
+  if (h->tables_from_host) return;  // qgd_*_tables: the caller's tables are already in d_table / d_cvals
+  if (h->host_controls)
+    throw QgdError(QGD_EUNSUPPORTED, "this problem has host-evaluated controls (QGD_CONTROL_HOST_TABLE): use the qgd_*_tables entry points");
   if (h->tab_key_nsteps == (int)h->nsteps && h->tab_key_m == m) return;
   const int Nt = (int)h->nsteps + 1;
   const size_t sz = (size_t)Nt * 2 * (m + 1) * std::max(h->P, 1);
@@ -405,6 +413,7 @@ void ensure_table(qgd_handle* h, int m) {
 }
 
 void compute_cvals(qgd_handle* h, int m, int B, const double* d_pcof) {
+  if (h->tables_from_host) return;
   const int Nt = (int)h->nsteps + 1;
   const size_t total = (size_t)B * Nt * 2 * (m + 1) * h->Nc;
   h->d_cvals.reserve(std::max<size_t>(total, 1) * 8);
@@ -609,6 +618,7 @@ int64_t qgd_control_n_coeff(const qgd_control_t* c) {
   if (c->type == QGD_CONTROL_GRAPE) base = 2 * c->n_amplitudes;
   else if (c->type == QGD_CONTROL_BSPLINE2) base = 2 * c->D1;
   else if (c->type == QGD_CONTROL_FORTRAN_BSPLINE) base = 2 * c->n_basis;
+  else if (c->type == QGD_CONTROL_HOST_TABLE) base = c->n_amplitudes;
   return c->n_carriers > 0 ? base * c->n_carriers : base;
 }
 int64_t qgd_problem_n_coeff(const qgd_problem_t* p) {
@@ -749,6 +759,72 @@ int qgd_eval_grad_forced(qgd_handle_t* h, const double* pcof, const double* targ
     }
     h->hist_valid = true;
     finish_timing(h, true, false);
+  });
+}
+
+// ---- host-evaluated controls: the caller's tables replace k_control_table / k_control_values --------------------
+namespace {
+struct HostTables {  // uploads the tables and routes ensure_table / compute_cvals around the device control kernels
+  qgd_handle* h;
+  HostTables(qgd_handle* h_, int B, int m, const double* cvals, const double* table) : h(h_) {
+    const size_t Nt = (size_t)h->nsteps + 1;
+    const size_t cbytes = (size_t)B * Nt * 2 * (m + 1) * std::max(h->Nc, 1) * 8;
+    h->d_cvals.reserve(cbytes);
+    if (h->Nc > 0) h2d(h, h->d_cvals.p, cvals, (size_t)B * Nt * 2 * (m + 1) * h->Nc * 8);
+    const size_t tbytes = Nt * 2 * (m + 1) * (size_t)std::max(h->P, 1) * 8;
+    h->d_table.reserve(tbytes);
+    if (table && h->P > 0) h2d(h, h->d_table.p, table, Nt * 2 * (m + 1) * (size_t)h->P * 8);
+    h->tab_key_nsteps = -1; h->tab_key_m = -1;  // the cached device-evaluated table is gone
+    h->tables_from_host = true;
+  }
+  ~HostTables() { h->tables_from_host = false; h->hist_valid = false; }
+};
+}  // namespace
+
+int qgd_eval_forward_tables(qgd_handle_t* h, int64_t n_batch, int32_t order, int64_t save_every, const double* cvals,
+                            double* history, double* final_state, int64_t* gmres_iters) {
+  return guarded([&]() {
+    require(h && cvals && n_batch >= 1, "bad arguments");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    check_order(order);
+    const int B = (int)n_batch, m = order / 2;
+    HostTables guard(h, B, m, cvals, nullptr);
+    run_forward(h, nullptr, B, order, save_every, gmres_iters != nullptr);
+    const int nslots = 1 + (int)(h->nsteps / save_every);
+    if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * nslots * h->ncol * B * 8);
+    if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
+    finish_timing(h, true, false);
+  });
+}
+
+int qgd_discrete_adjoint_tables(qgd_handle_t* h, int64_t n_batch, int32_t order, const double* cvals, const double* table,
+                                const double* target, double* grad, double* infidelity, double* guard_penalty) {
+  return guarded([&]() {
+    require(h && cvals && table && target && n_batch >= 1, "bad arguments");
+    if (h->ncol != h->nic) throw QgdError(QGD_ESTATE, "column-sharded handle: the table entry points need all columns");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    check_order(order);
+    const int B = (int)n_batch, m = order / 2;
+    HostTables guard(h, B, m, cvals, table);
+    h->d_target.reserve((size_t)h->N2 * h->nic * 8);
+    h2d(h, h->d_target.p, target, (size_t)h->N2 * h->nic * 8);
+    run_forward(h, nullptr, B, order, 1, false);
+    run_guard(h, B, order, false);
+    h->d_final_all.reserve((size_t)h->N2 * h->nic * B * 8);
+    CUDA_CHECK(cudaMemcpyAsync(h->d_final_all.p, h->d_final.p, (size_t)h->N2 * h->nic * B * 8, cudaMemcpyDeviceToDevice, h->stream));
+    h->d_infid.reserve((size_t)B * 8); h->d_guard.reserve((size_t)B * 8);
+    h->d_grad.reserve((size_t)std::max(h->P, 1) * B * 8);
+    run_adjoint(h, B, order, h->d_target.as<double>(), false, false, h->d_grad.as<double>(), h->d_infid.as<double>(),
+                h->d_guard.as<double>());
+    if (grad) d2h(h, grad, h->d_grad.p, (size_t)h->P * B * 8);
+    if (infidelity) d2h(h, infidelity, h->d_infid.p, (size_t)B * 8);
+    if (guard_penalty) d2h(h, guard_penalty, h->d_guard.p, (size_t)B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    finish_timing(h, true, true);
   });
 }
 

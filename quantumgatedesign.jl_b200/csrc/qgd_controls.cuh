@@ -14,6 +14,7 @@
 #define QGD_CONTROL_GRAPE 1
 #define QGD_CONTROL_BSPLINE2 2
 #define QGD_CONTROL_FORTRAN_BSPLINE 3
+#define QGD_CONTROL_HOST_TABLE 4
 #define QGD_FBS_MAXORDER 20
 
 namespace qgd {

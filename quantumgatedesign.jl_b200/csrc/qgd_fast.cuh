@@ -43,6 +43,9 @@ namespace qgd {
 #ifndef QGD_BWD_VARIANT
 #define QGD_BWD_VARIANT 3
 #endif
+#ifndef QGD_BWD_MERGE_SIDES
+#define QGD_BWD_MERGE_SIDES 0  // the implicit-side and explicit-side gradient sweeps of an adjoint step share one inlined copy
+#endif
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
@@ -1003,30 +1006,39 @@ template <int EL, int NC, int VARIANT, class OP>
 __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
                                   int restart, int maxiter) {
   constexpr int BLK = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 4;
+  constexpr int CHK = 2 * EL;  // k <= restart <= 2N <= 64 EL: CHK chunks of 32 rows cover a Hessenberg column
   const int lane = c.lane;
-  Vec<EL> v, w;
-  op.apply(x, w);
-#pragma unroll
-  for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
-  precond_fast<EL, NC>(R, v);
-  double beta2 = warp_allsum(vdot_local<EL>(v, v));
-  double rbeta = rsqrt(beta2), beta = beta2 * rbeta;
-  vscale(v, rbeta);
-  basis_store<EL>(c, 0, v);
-  double res_beta = beta, accum = 1.0;
   // residual estimate beta / sqrt(accum) against tol, tested as beta^2 <= tol^2 accum (no square root on the
   // critical path of an iteration; the two tests differ only when the estimate is within an ulp of tol)
   const double tol2 = tol * tol;
-  double res_beta2 = beta2;
-  bool conv = !(res_beta2 > tol2);
-  __syncwarp();
-  if (lane == 0) c.nullv[0] = 1.0;
-  __syncwarp();
+  double res_beta = 0.0, res_beta2 = 0.0, accum = 1.0;
+  bool conv = false, first = true, start = true;
   int k = 1, it = 0;
-  constexpr int CHK = 2 * EL;  // k <= restart <= 2N <= 64 EL: CHK chunks of 32 rows cover a Hessenberg column
-  while (it < maxiter && !conv) {
-    op.apply(v, w);  // expand!
-    precond_fast<EL, NC>(R, w);
+  Vec<EL> v = x, w;
+  // ONE inlined copy of the operator application serves the initial residual, the Arnoldi steps and the restarts
+  // (three copies cost 20 KB of instruction cache in a kernel whose hot loop has to live in 32 KB)
+#pragma unroll 1
+  for (;;) {
+    op.apply(v, w);
+    if (start) {  // residual of the current iterate x (init!, init_residual!)
+#pragma unroll
+      for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
+      precond_fast<EL, NC>(R, v);
+      const double beta2 = warp_allsum(vdot_local<EL>(v, v));
+      const double rbeta = rsqrt(beta2);
+      vscale(v, rbeta);
+      basis_store<EL>(c, 0, v);
+      accum = 1.0; res_beta = beta2 * rbeta; res_beta2 = beta2;
+      if (first) conv = !(beta2 > tol2);  // at a restart residual.current keeps its value, as in the package
+      first = false; start = false;
+      k = 1;
+      __syncwarp();
+      if (lane == 0) c.nullv[0] = 1.0;
+      __syncwarp();
+      if (conv || it >= maxiter) break;
+      continue;
+    }
+    precond_fast<EL, NC>(R, w);  // expand!
     gs_orthogonalize<EL, BLK, VARIANT>(c, k, w);
     // ||w||^2 and the null-vector recurrence <nullvec[0..k), H[0..k, k-1]> (update_residual!)
     double dpart = 0.0, hreg[CHK];
@@ -1056,9 +1068,11 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
     accum = fma(nv, nv, accum);
     conv = !(res_beta2 > tol2 * accum);
     k += 1;
+    it += 1;
     v = w;
     __syncwarp();
-    if (k == restart + 1 || conv) {
+    const bool done = conv || it >= maxiter;
+    if (k == restart + 1 || done) {  // x only at the end of the iterations and at a restart
       const int width = k - 1;
       if constexpr (QGD_QR_LEAN) qr_solve_lean(c, width, res_beta);
       else qr_solve_fast(c, width, res_beta);
@@ -1070,23 +1084,10 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
         vaxpy(x, c.g[j], vi);
         if (j + 1 < width) vi = vn;
       }
-      k = 1;
-      if (!conv) {  // restart (residual.current keeps its value, as in the package)
-        op.apply(x, w);
-#pragma unroll
-        for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
-        precond_fast<EL, NC>(R, v);
-        beta2 = warp_allsum(vdot_local<EL>(v, v));
-        rbeta = rsqrt(beta2); beta = beta2 * rbeta;
-        vscale(v, rbeta);
-        basis_store<EL>(c, 0, v);
-        accum = 1.0; res_beta = beta; res_beta2 = beta2;
-        __syncwarp();
-        if (lane == 0) c.nullv[0] = 1.0;
-      }
       __syncwarp();
+      if (done) break;
+      v = x; start = true;  // restart from the residual of the updated iterate
     }
-    it += 1;
   }
   return it;
 }
@@ -1315,8 +1316,10 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
     }
     load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n_hi + 1) * cv_stride);
     for (int n = n_hi; n >= n_lo; --n) {
-      double gK[M][NC], gS[M][NC];
       Vec<EL> w0, rhs;
+#if !QGD_BWD_MERGE_SIDES
+      {
+      double gK[M][NC], gS[M][NC];
       // ---- implicit side: time level n+1 (its control values are the ones currently loaded)
 #pragma unroll
       for (int r = 0; r < M; ++r)
@@ -1350,6 +1353,35 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       __syncwarp();
       accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
       __syncwarp();
+      }
+#else
+      // side 0: implicit side, time level n+1 (its control values are the ones currently loaded), -LHS coefficients;
+      // side 1: explicit side, time level n, RHS coefficients; rhs = R(t_n)^T lambda_{n+1}.  One rolled loop: a second
+      // inlined copy of the gradient sweep would cost 21 KB of instruction cache.
+#pragma unroll 1
+      for (int side = 0; side < 2; ++side) {
+        double gK[M][NC], gS[M][NC], alpha[M + 1];
+#pragma unroll
+        for (int j = 0; j <= M; ++j) alpha[j] = side ? a_rhs[j] : a_imp[j];
+#pragma unroll
+        for (int r = 0; r < M; ++r)
+#pragma unroll
+          for (int k = 0; k < NC; ++k) { gK[r][k] = 0.0; gS[r][k] = 0.0; }
+        const int lvl = n + 1 - side;
+        if (side) load_cv_fast<EL, M, NC>(c, cvb + (size_t)n * cv_stride);
+        adj_fast<EL, M, NC, true>(c, R, lam, alpha, rhs, hist + slot_sz * lvl, gK, gS);
+#pragma unroll
+        for (int r = 0; r < M; ++r)
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            const double sK = warp_allsum(gK[r][k]), sS = warp_allsum(gS[r][k]);
+            if (lane == 0) { gKs[r * NC + k] = sK; gSs[r * NC + k] = sS; }
+          }
+        __syncwarp();
+        accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)lvl * tab_stride, gKs, gSs, gacc);
+        __syncwarp();
+      }
+#endif
       if (n >= 1) {
         // guard forcing f_n = -(2 dt/tf) W w_n (interior point: trapezoid weight 1), W diagonal
         vload_cs(w0, hist + slot_sz * n, N, lane);

@@ -75,6 +75,8 @@ struct qgd_handle {
   // register-operator fast path (qgd_fast.cuh): structure test done once at creation
   bool fast_ok = false;
   int fast_el = 0;
+  bool host_controls = false;     // some control is QGD_CONTROL_HOST_TABLE: only the qgd_*_tables entry points work
+  bool tables_from_host = false;  // inside a qgd_*_tables call: d_cvals / d_table hold the caller's tables
   bool l2_carved = false;  // cudaLimitPersistingL2CacheSize set for the workspace window (qgd_fast_inst.cuh)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   qgd_stats_t stats{};

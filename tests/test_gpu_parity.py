@@ -327,3 +327,75 @@ def test_eval_grad_forced_vs_oracle_and_adjoint(q, O, name):
     ga = q.discrete_adjoint(prob, controls, pcof, target, order=order)
     assert rel(ga, gf) < 1e-9
     q.backend.clear_handles()
+
+
+# ---- host-evaluated controls through the table entry points ----------------------------
+def _tables_from_device(h, pcofs, nsteps, tf, m):
+    """cvals / table of the qgd_*_tables entry points from the device's own control kernels (eval_controls)."""
+    from math import factorial
+
+    pcofs = np.asarray(pcofs, dtype=np.float64)
+    if pcofs.ndim == 1:
+        pcofs = pcofs[:, None]
+    times = np.arange(nsteps + 1) * tf / nsteps
+    inv_fact = np.array([1.0 / factorial(j) for j in range(m + 1)])
+    B = pcofs.shape[1]
+    cvals = np.zeros((h.Nc, m + 1, 2, nsteps + 1, B), order="F")
+    table = np.zeros((h.P, m + 1, 2, nsteps + 1), order="F")
+    for b in range(B):
+        # p, q come Taylor-scaled (fill_p_mat!), the parameter gradients un-scaled (eval_grad_p_derivative!)
+        p, qq, gp, gq = h.eval_controls(pcofs[:, b], times, m + 1, want_grad=True)  # [nderiv, Nc, nt], [P, nderiv, nt]
+        cvals[:, :, 0, :, b] = np.transpose(p, (1, 0, 2))
+        cvals[:, :, 1, :, b] = np.transpose(qq, (1, 0, 2))
+        if b == 0:
+            table[:, :, 0, :] = gp * inv_fact[None, :, None]
+            table[:, :, 1, :] = gq * inv_fact[None, :, None]
+    return cvals, table
+
+
+@pytest.mark.parametrize("name", ["cnot2", "cnot3_333", "rabi_carrier"])
+def test_host_table_controls_match_device_controls(q, O, name):
+    """The same problem with its controls declared host-evaluated (QGD_CONTROL_HOST_TABLE) and fed through
+    qgd_discrete_adjoint_tables reproduces the device-evaluated gradient / infidelity / guard penalty, and the
+    oracle's, for a batch of two control vectors."""
+    prob, controls, pcof, target, order = _cases(q)[name]
+    m = order // 2
+    cl = q.as_control_list(controls)
+    rng = np.random.default_rng(11)
+    pcofs = np.stack([pcof, pcof * (1.0 + 0.3 * rng.standard_normal(len(pcof)))], axis=1)
+    hd = q.Handle(prob, controls)
+    direct = hd.discrete_adjoint(pcofs, q.complex_to_real(target), order=order)
+    cvals, table = _tables_from_device(hd, pcofs, prob.nsteps, prob.tf, m)
+    host_controls = [q.HostEvaluatedControl(c.N_coeff, c.tf, None) for c in cl]
+    hh = q.Handle(prob, host_controls)
+    out = hh.discrete_adjoint_tables(cvals, table, q.complex_to_real(target), order=order)
+    assert rel(out["grad"], direct["grad"]) < 1e-12
+    assert rel(out["infidelity"], direct["infidelity"]) < 1e-12
+    assert np.abs(out["guard_penalty"] - direct["guard_penalty"]).max() <= 1e-12 * max(1.0, np.abs(direct["guard_penalty"]).max())
+    ref = O.discrete_adjoint(prob, controls, pcofs[:, 1], target, order=order)
+    assert rel(out["grad"][:, 1], ref["grad"]) < RTOL
+    with pytest.raises(q.QGDError):  # pcof entry points cannot evaluate host controls
+        hh.discrete_adjoint(pcofs, q.complex_to_real(target), order=order)
+    hd.close(); hh.close()
+
+
+def test_sincos_control_host_tables_gradient(q):
+    """SinCosControl (src/Controls/sincos_control.jl:1-27), a family without a device kernel: gradient through the
+    host-table path vs central finite differences of the infidelity computed through the same path
+    (the reference's check, test/GradientTests/compare_gradients.jl: 1e-9 relative to the gradient norm ... here 1e-7
+    with h = 1e-5 on a short problem)."""
+    prob = q.construct_rand_prob(4, 2, tf=1.0, nsteps=10, gmres_abstol=1e-15, gmres_reltol=1e-15)
+    controls = [q.SinCosControl(prob.tf, frequency=3.0), q.SinCosControl(prob.tf, frequency=5.0)]
+    rng = np.random.default_rng(3)
+    pcof = rng.random(4)
+    target = rng.random((4, 4)) + 1j * rng.random((4, 4))
+    order = 6
+    g = q.discrete_adjoint(prob, controls, pcof, target, order=order)
+    fd = np.zeros_like(g)
+    hstep = 1e-5
+    for i in range(len(pcof)):
+        e = np.zeros_like(pcof); e[i] = hstep
+        fd[i] = (q.infidelity(prob, controls, pcof + e, target, order=order)
+                 - q.infidelity(prob, controls, pcof - e, target, order=order)) / (2 * hstep)
+    assert rel(g, fd) < 1e-7
+    q.backend.clear_handles()
