@@ -49,8 +49,10 @@ function qgd_control(c::CarrierControl)
     return QgdControl(b.type, 0, b.tf, b.n_amplitudes, b.D1, b.degree, b.n_basis,
                       length(c.carrier_frequencies), pointer(c.carrier_frequencies))
 end
-qgd_control(c::AbstractControl) =
-    throw(ArgumentError("$(typeof(c)) is not on the B200 hot path (GRAPE, BSpline2, FortranBSpline, Carrier)"))
+# every other AbstractControl (GeneralBSplineControl, HermiteControl, HermiteCarrierControl, ...): no device kernel,
+# the host evaluates the control protocol and passes tables (QGD_CONTROL_HOST_TABLE = 4, n_amplitudes = N_coeff)
+qgd_control(c::AbstractControl) = QgdControl(4, 0, c.tf, c.N_coeff, 0, 0, 0, 0, C_NULL)
+is_host_control(c::AbstractControl) = qgd_control(c).type == 4
 
 struct QgdProblem
     N_tot_levels::Int64
@@ -141,16 +143,74 @@ _ptr_or_null(A::Array{Float64}) = pointer(A)
 # ---- eval_forward!  (src/forward_evolution.jl:33-70) ---------------------------------------------------
 function eval_forward_b200!(uv_history::Array{Float64,4}, prob::SchrodingerProb, controls,
         pcof::Vector{Float64}; order::Int=2, saveEveryNsteps::Int=1, forcing=missing, device::Integer=-1)
-    ismissing(forcing) || throw(ArgumentError("forced solves are not on the B200 path"))
     m = div(order, 2)
     @assert size(uv_history) == (prob.real_system_size, 1 + m, 1 + div(prob.nsteps, saveEveryNsteps), prob.N_initial_conditions)
     h = b200_handle(prob, controls; device=device)
-    GC.@preserve uv_history pcof begin
-        qgd_check(ccall((:qgd_eval_forward, libqgd), Cint,
-            (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
-            h.ptr, pcof, 1, order, saveEveryNsteps, uv_history, C_NULL, C_NULL))
+    GC.@preserve uv_history pcof forcing begin
+        if any(is_host_control, controls)
+            cvals, _ = control_tables(controls, pcof, prob.tf, prob.nsteps, m)
+            qgd_check(ccall((:qgd_eval_forward_tables, libqgd), Cint,
+                (Ptr{Cvoid}, Int64, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                h.ptr, 1, order, saveEveryNsteps, cvals, uv_history, C_NULL, C_NULL))
+        elseif ismissing(forcing)
+            qgd_check(ccall((:qgd_eval_forward, libqgd), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                h.ptr, pcof, 1, order, saveEveryNsteps, uv_history, C_NULL, C_NULL))
+        else  # forcing::Array{Float64,4} [2N, m, 1+nsteps, nic]  (src/forward_evolution.jl:118-129)
+            qgd_check(ccall((:qgd_eval_forward_forced, libqgd), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                h.ptr, pcof, 1, order, saveEveryNsteps, forcing, uv_history, C_NULL, C_NULL))
+        end
     end
     return nothing
+end
+
+# ---- eval_grad_forced  (src/eval_grad_forced.jl:18-195): P forced solves batched on the device -----------
+function eval_grad_forced_b200(prob::SchrodingerProb, controls, pcof::Vector{Float64}, target::AbstractMatrix{<:Number};
+        order::Int=2, cost_type=:Infidelity, device::Integer=-1)
+    cost_type == :Infidelity || throw("Invalid cost type: $cost_type")
+    R = Matrix{Float64}(complex_to_real(target))
+    h = b200_handle(prob, controls; device=device)
+    grad = zeros(length(pcof))
+    qgd_check(ccall((:qgd_eval_grad_forced, libqgd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}),
+        h.ptr, pcof, R, order, grad))
+    return grad
+end
+
+# ---- host-evaluated controls: tables from the reference's own control protocol (Control.jl:99-149) ------
+function control_tables(controls, pcof, tf, nsteps, m)
+    Nc, P = length(controls), get_number_of_control_parameters(controls)
+    cvals = zeros(Nc, 1 + m, 2, 1 + nsteps, 1)
+    table = zeros(P, 1 + m, 2, 1 + nsteps)
+    pmat = zeros(1 + m, Nc); qmat = zeros(1 + m, Nc)
+    for n in 0:nsteps
+        t = n * tf / nsteps
+        fill_p_mat!(pmat, controls, t, pcof); fill_q_mat!(qmat, controls, t, pcof)   # Taylor-scaled p^(j)/j!
+        cvals[:, :, 1, 1+n, 1] .= pmat'; cvals[:, :, 2, 1+n, 1] .= qmat'
+        offset = 0
+        for c in controls
+            sl = offset+1:offset+c.N_coeff
+            for j in 0:m
+                eval_grad_p_derivative!(view(table, sl, 1+j, 1, 1+n), c, t, pcof[sl], j)
+                eval_grad_q_derivative!(view(table, sl, 1+j, 2, 1+n), c, t, pcof[sl], j)
+                table[sl, 1+j, :, 1+n] ./= factorial(j)
+            end
+            offset += c.N_coeff
+        end
+    end
+    return cvals, table
+end
+
+function discrete_adjoint_b200_tables(prob::SchrodingerProb, controls, pcof::Vector{Float64},
+        target::AbstractMatrix{<:Number}; order::Int=2, device::Integer=-1)
+    R = Matrix{Float64}(complex_to_real(target))
+    h = b200_handle(prob, controls; device=device)
+    cvals, table = control_tables(controls, pcof, prob.tf, prob.nsteps, div(order, 2))
+    grad = zeros(length(pcof)); infid = Ref(0.0); guard = Ref(0.0)
+    qgd_check(ccall((:qgd_discrete_adjoint_tables, libqgd), Cint,
+        (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
+        h.ptr, 1, order, cvals, table, R, grad, infid, guard))
+    return grad, infid[], guard[]
 end
 
 # ---- discrete_adjoint!  (src/eval_grad_discrete_adjoint.jl:107-160) ------------------------------------

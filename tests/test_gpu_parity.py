@@ -399,3 +399,32 @@ def test_sincos_control_host_tables_gradient(q):
                  - q.infidelity(prob, controls, pcof - e, target, order=order)) / (2 * hstep)
     assert rel(g, fd) < 1e-7
     q.backend.clear_handles()
+
+
+# ---- step-size studies on the GPU forward solve ----------------------------------------
+def test_get_histories_richardson_orders(q):
+    """get_histories (src/Tests/test_convergence.jl:20-146) on the reference's random N=4 problem (tf=10, base 40 steps,
+    test/ConvergenceTests/forward_convergence.jl:204-220): the Richardson error of consecutive refinements falls at
+    2^order per halving until roundoff."""
+    prob = q.construct_rand_prob(4, 1, tf=10.0, nsteps=40, gmres_abstol=1e-15, gmres_reltol=1e-15)
+    ctl = q.FortranBSplineControl(8, 12, prob.tf)
+    pcof = 0.2 * np.random.default_rng(2).standard_normal(ctl.N_coeff)
+    res = q.get_histories(prob, ctl, pcof, 4, orders=(2, 4, 6))
+    for order in (2, 4, 6):
+        s = res[f"Order {order} (QGD)"]
+        assert s["nsteps"] == [40, 80, 160, 320]
+        assert all(h.shape == (4, 41, 4) for h in s["histories"])  # complex [N, 1 + base_nsteps, nic] on the base grid
+        e = np.array(s["richardson_errors"][1:])
+        rates = np.log2(e[:-1] / e[1:])
+        print("order", order, "richardson errors", e, "rates", rates)
+        assert all(r > order - 0.7 for r in rates[e[1:] > 1e-11]), (order, e, rates)
+    q.backend.clear_handles()
+
+
+def test_estimate_timesteps_per_period(q):
+    """estimate_timesteps_per_period (src/calculate_timestep.jl:58-98): errors decrease with the steps per period."""
+    prob = q.construct_rand_prob(4, 2, tf=3.0, nsteps=10, gmres_abstol=1e-14, gmres_reltol=1e-14)
+    errs = q.estimate_timesteps_per_period(prob, [0.5, 0.3], 4, exponents=range(0, 6))
+    # order 4: once resolved, every doubling of the steps per period gains about 2^4
+    assert len(errs) == 5 and errs[-1] < errs[0] * 1e-3 and errs[-2] / errs[-1] > 8.0, errs
+    q.backend.clear_handles()
