@@ -43,6 +43,14 @@ namespace qgd {
 #ifndef QGD_BWD_VARIANT
 #define QGD_BWD_VARIANT 3
 #endif
+// Lean least squares (qr_solve_lean) and compact per-warp shared memory: the rotated right-hand side `g` lives in the
+// gather buffer (idle during the least-squares solve), the subdiagonal of H is read from the packed matrix, the
+// adjoint sweep's gradient accumulator lives in L2 -- which frees 3.7 KB per warp and lets 24 instead of 16 Krylov
+// vectors stay in shared memory.
+#ifndef QGD_QR_LEAN
+#define QGD_QR_LEAN 1
+#endif
+#define QGD_COMPACT_SMEM (QGD_QR_LEAN && QGD_MGS_BLOCK > 1)
 #ifndef QGD_BWD_MERGE_SIDES
 #define QGD_BWD_MERGE_SIDES 0  // the implicit-side and explicit-side gradient sweeps of an adjoint step share one inlined copy
 #endif
@@ -160,8 +168,13 @@ struct FastCtx {
 };
 template <int EL, int M, int NC>
 __host__ __device__ constexpr int fast_fixed_doubles(int N2) {
+#if QGD_COMPACT_SMEM
+  // xs (+ g, gKs, gSs aliased) + cv + nullv + hcol
+  return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + (N2 + 2 + 8);
+#else
   // xs + cv + nullv + rot + g
   return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
+#endif
 }
 
 template <int EL>
@@ -270,7 +283,9 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
 // out = what_0 = (sum_j alpha_j W_j)^T x.  GRAD: accumulate per lane
 //   gK[r][k] += IPK_k(w_i, what_{j+1})/(j+1), gS[r][k] += IPS_k(w_i, what_{j+1})/(j+1), r = j - i,
 // with w_i the forward Taylor columns of the same time level (hist, global).  SURVEY A.6.
-template <int EL, int M, int NC, bool GRAD>
+// LAST: this is the last use of the history level (evict-first load); otherwise the level is read once more by the
+// next adjoint step and is loaded with the default L2 policy so that it is still resident then.
+template <int EL, int M, int NC, bool GRAD, bool LAST = true>
 __device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
                                          Vec<EL>& out, const double* hist, double (&gK)[M][NC], double (&gS)[M][NC]) {
   const int lane = c.lane, N = c.N, N2 = c.N2;
@@ -280,7 +295,10 @@ __device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, 
   Vec<EL> wh[M];
   if (GRAD) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) vload_cs(wh[i], hist + (size_t)i * N2, N, lane);
+    for (int i = 0; i < M; ++i) {
+      if constexpr (LAST) vload_cs(wh[i], hist + (size_t)i * N2, N, lane);
+      else vload_cg(wh[i], hist + (size_t)i * N2, N, lane);
+    }
   }
   __syncwarp();
 #pragma unroll
@@ -882,11 +900,8 @@ __device__ __forceinline__ void qr_solve_fast(const CTX& c, int width, double be
 // that the pivot owner's register is indexed statically, the rows of H two and three rotations ahead are prefetched
 // straight into registers, the special cases of givensAlgorithm fold into the sign of one reciprocal square root
 // (1 / r_ii IS that reciprocal square root: no division), and lane 0's stores are predicated, not branched.
-#ifndef QGD_QR_LEAN
-#define QGD_QR_LEAN 1
-#endif
 template <int S0, int CH>
-__device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* const (&colp)[CH], const double* sub, double* dinv,
+__device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* const (&colp)[CH], double* dinv,
                                                   double* g, double& gcur, int width, int nsl, int lane) {
   const int i0 = 32 * S0;
   if (i0 >= width) return;
@@ -901,7 +916,7 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
   };
   auto rotate = [&](int i, const double (&lo)[CH]) {
     const double a = __shfl_sync(FULL_MASK, top[S0], i & 31);
-    const double b = sub[i];
+    const double b = __shfl_sync(FULL_MASK, lo[S0], i & 31);  // H[i+1][i], the row of the pivot owner's own column
     double rr = rsqrt(fma(a, a, b * b));
     // LinearAlgebra.givensAlgorithm: r = +-sqrt(a^2 + b^2), negative only when |a| > |b| and a < 0
     rr = (a < 0.0 && fabs(a) > fabs(b)) ? -rr : rr;
@@ -982,10 +997,10 @@ __device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double be
     top[s] = j < width ? __ldcg(colp[s]) : 0.0;
   }
   double gcur = beta;
-  qr_rotation_phase<0, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
-  qr_rotation_phase<1, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
-  qr_rotation_phase<2, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
-  qr_rotation_phase<3, CH>(top, colp, c.sub, dinv, c.g, gcur, width, nsl, lane);
+  qr_rotation_phase<0, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
+  qr_rotation_phase<1, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
+  qr_rotation_phase<2, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
+  qr_rotation_phase<3, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
   __threadfence_block();
   __syncwarp();  // R (L2), dinv and g (shared memory) of all lanes are visible
   double gi[CH];
@@ -1063,7 +1078,11 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
         const int i = lane + 32 * s;
         if (i < k) hc[i] = hreg[s];
       }
+#if QGD_COMPACT_SMEM
+      if (lane == 0) { hc[k] = nrm; c.nullv[k] = nv; }
+#else
       if (lane == 0) { hc[k] = nrm; c.sub[k - 1] = nrm; c.nullv[k] = nv; }
+#endif
     }
     accum = fma(nv, nv, accum);
     conv = !(res_beta2 > tol2 * accum);
@@ -1178,9 +1197,16 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   double* w = reinterpret_cast<double*>(smem + 16) + (size_t)warp * a.warp_smem_doubles;
   c.xs = reinterpret_cast<double2*>(w); w += FastCtx<EL>::kRingDoubles;
   c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
+#if QGD_COMPACT_SMEM
+  static_assert(FastCtx<EL>::kRingDoubles >= 64 * EL + 2, "g (2N + 2 doubles) aliases the gather buffer");
+  c.rot = nullptr; c.hcol = w; c.sub = nullptr; w += d.N2 + 2 + 8;
+  c.nullv = w; w += d.N2 + 2;
+  c.g = reinterpret_cast<double*>(c.xs);
+#else
   c.rot = reinterpret_cast<double2*>(w); c.hcol = w; c.sub = w + d.N2 + 10; w += 2 * (d.N2 + 2 + 8);
   c.nullv = w; w += d.N2 + 2;
   c.g = w; w += d.N2 + 2;
+#endif
   c.Vs = reinterpret_cast<double2*>(w); w += (size_t)a.ks * 2 * 32 * EL;
   *extra = w;
   const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -1264,7 +1290,14 @@ __device__ __forceinline__ void accumulate_grad_fast(int lane, int P, const QgdD
         s = fma(table_n[((size_t)0 * nd + r) * P + off + t], gKs[r * NC + k], s);
         s = fma(table_n[((size_t)1 * nd + r) * P + off + t], gSs[r * NC + k], s);
       }
+#if QGD_COMPACT_SMEM
+      // the accumulator is the L2-resident gradient partial of the column (it migrates between SMs with the tickets).
+      // One lane of one warp owns an entry at any time, so the reduction instruction is deterministic; unlike a
+      // load-subtract-store it does not wait for the L2 round trip.
+      atomicAdd(gacc + off + t, -s);
+#else
       gacc[off + t] -= s;
+#endif
     }
   }
 }
@@ -1287,9 +1320,18 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
   const size_t cv_stride = (size_t)2 * (M + 1) * NC;
   const size_t slot_sz = (size_t)N2 * (M + 1);
   const size_t tab_stride = (size_t)2 * (M + 1) * P;
+#if QGD_COMPACT_SMEM
+  // reduced g^K, g^S [M][NC] each: in the gather buffer (idle between the gradient sweep and the contraction with the
+  // control basis table); the gradient partial itself accumulates in L2 (gcol), touched once per time step
+  static_assert(FastCtx<EL>::kRingDoubles >= 2 * M * NC, "gKs / gSs alias the gather buffer");
+  double* gKs = reinterpret_cast<double*>(c.xs);
+  double* gSs = gKs + M * NC;
+  (void)extra;
+#else
   double* gacc = extra;          // [P]
   double* gKs = gacc + P;        // [M][NC] reduced g^K
   double* gSs = gKs + M * NC;    // [M][NC] reduced g^S
+#endif
   const AdjOpFast<EL, M, NC> op{c, R, a_lhs};
   const double fsc = -2.0 * d.dt / d.tf;
   const int S = a.seg_steps, nseg = (d.nsteps + S - 1) / S;
@@ -1305,13 +1347,18 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
     double* carry = a.carry + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b);   // lambda between segments
     const int n_hi = d.nsteps - 1 - seg * S, n_lo = max(n_hi - S + 1, 0);
     Vec<EL> lam;
+#if QGD_COMPACT_SMEM
+    double* gacc = gcol;
+#endif
     if (seg == 0) {
       for (int t = lane; t < P; t += 32) gacc[t] = 0.0;
       vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
       if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, lane);
     } else {
       wait_segment(a.progress + item, seg, lane);
+#if !QGD_COMPACT_SMEM
       for (int t = lane; t < P; t += 32) gacc[t] = __ldcg(gcol + t);
+#endif
       vload_cg(lam, carry, N, lane);
     }
     load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n_hi + 1) * cv_stride);
@@ -1342,7 +1389,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       for (int r = 0; r < M; ++r)
 #pragma unroll
         for (int k = 0; k < NC; ++k) { gK[r][k] = 0.0; gS[r][k] = 0.0; }
-      adj_fast<EL, M, NC, true>(c, R, lam, a_rhs, rhs, hist + slot_sz * n, gK, gS);  // rhs = R(t_n)^T lambda_{n+1}
+      adj_fast<EL, M, NC, true, false>(c, R, lam, a_rhs, rhs, hist + slot_sz * n, gK, gS);  // rhs = R(t_n)^T lambda_{n+1}
 #pragma unroll
       for (int r = 0; r < M; ++r)
 #pragma unroll
@@ -1384,7 +1431,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
 #endif
       if (n >= 1) {
         // guard forcing f_n = -(2 dt/tf) W w_n (interior point: trapezoid weight 1), W diagonal
-        vload_cs(w0, hist + slot_sz * n, N, lane);
+        vload_cg(w0, hist + slot_sz * n, N, lane);
 #pragma unroll
         for (int e = 0; e < EL; ++e) {
           rhs.u[e] = fma(fsc, R.wu[e] * w0.u[e], rhs.u[e]);
@@ -1397,7 +1444,9 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       }
     }
     __syncwarp();
+#if !QGD_COMPACT_SMEM
     for (int t = lane; t < P; t += 32) gcol[t] = gacc[t];
+#endif
     if (seg < nseg - 1) vstore(lam, carry, N, lane);
     publish_segment(a.progress + item, seg, lane);
   }

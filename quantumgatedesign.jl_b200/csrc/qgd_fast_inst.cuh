@@ -117,7 +117,7 @@ void launch_forward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
 }
 template <int EL, int M, int NC>
 void launch_backward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
-  const int extra = d.P + 2 * M * NC;
+  const int extra = QGD_COMPACT_SMEM ? 0 : d.P + 2 * M * NC;
   FastCfg L = plan_fast(h, k_backward_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)a.B * d.ncol, extra, d.N2);
   ensure_krylov_fast(h, L, EL, d.N2, a);
   launch_sweep(h, k_backward_fast<EL, M, NC>, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
