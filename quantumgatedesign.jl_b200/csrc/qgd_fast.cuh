@@ -52,7 +52,7 @@ namespace qgd {
 #endif
 #define QGD_COMPACT_SMEM (QGD_QR_LEAN && QGD_MGS_BLOCK > 1)
 #ifndef QGD_BWD_MERGE_SIDES
-#define QGD_BWD_MERGE_SIDES 0  // the implicit-side and explicit-side gradient sweeps of an adjoint step share one inlined copy
+#define QGD_BWD_MERGE_SIDES 0  // gradient sweeps of an adjoint step: 0 two inlined copies, 1 one rolled loop, 2 one real function
 #endif
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -285,9 +285,10 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
 // with w_i the forward Taylor columns of the same time level (hist, global).  SURVEY A.6.
 // LAST: this is the last use of the history level (evict-first load); otherwise the level is read once more by the
 // next adjoint step and is loaded with the default L2 policy so that it is still resident then.
-template <int EL, int M, int NC, bool GRAD, bool LAST = true>
+template <int EL, int M, int NC, bool GRAD>
 __device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
-                                         Vec<EL>& out, const double* hist, double (&gK)[M][NC], double (&gS)[M][NC]) {
+                                         Vec<EL>& out, const double* hist, double (&gK)[M][NC], double (&gS)[M][NC],
+                                         bool last_use = true) {
   const int lane = c.lane, N = c.N, N2 = c.N2;
   Vec<EL> what[M + 1];
 #pragma unroll
@@ -295,9 +296,12 @@ __device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, 
   Vec<EL> wh[M];
   if (GRAD) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
-      if constexpr (LAST) vload_cs(wh[i], hist + (size_t)i * N2, N, lane);
-      else vload_cg(wh[i], hist + (size_t)i * N2, N, lane);
+    if (last_use) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) vload_cs(wh[i], hist + (size_t)i * N2, N, lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < M; ++i) vload_cg(wh[i], hist + (size_t)i * N2, N, lane);
     }
   }
   __syncwarp();
@@ -1275,6 +1279,31 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
   if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }
 
+// One side of an adjoint step as a real (not inlined) function: out = (sum_j sign alpha_j W_j(t))^T lam together with
+// the reduced inner products g^K, g^S [M][NC] of that time level (left in gKs / gSs, shared memory).  It runs twice per
+// time step; inlining it twice costs 21 KB of instruction cache in a kernel whose GMRES loop has to stay resident, and
+// rolling the two calls into a loop spills registers into that loop.
+template <int EL, int M, int NC>
+__device__ __noinline__ void grad_side_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& lam, const double* alpha_src,
+                                            double sign, Vec<EL>& out, const double* hist, bool last_use, double* gKs, double* gSs) {
+  double gK[M][NC], gS[M][NC], alpha[M + 1];
+#pragma unroll
+  for (int j = 0; j <= M; ++j) alpha[j] = sign * alpha_src[j];
+#pragma unroll
+  for (int r = 0; r < M; ++r)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { gK[r][k] = 0.0; gS[r][k] = 0.0; }
+  adj_fast<EL, M, NC, true>(c, R, lam, alpha, out, hist, gK, gS, last_use);
+#pragma unroll
+  for (int r = 0; r < M; ++r)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const double sK = warp_allsum(gK[r][k]), sS = warp_allsum(gS[r][k]);
+      if (c.lane == 0) { gKs[r * NC + k] = sK; gSs[r * NC + k] = sS; }
+    }
+  __syncwarp();
+}
+
 // grad_acc[theta] -= sum_r table_p[r][theta] gK[r][k(theta)] + table_q[r][theta] gS[r][k(theta)]
 template <int M, int NC>
 __device__ __forceinline__ void accumulate_grad_fast(int lane, int P, const QgdDevControl* ctrls, const double* table_n,
@@ -1311,8 +1340,9 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
   const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra, tmem_base);
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2, Nt = d.nsteps + 1, P = d.P;
-  RegOps<EL, NC> R;
-  load_regops<EL, NC>(R, d, lane, 1);
+  RegOps<EL, NC> R0;
+  load_regops<EL, NC>(R0, d, lane, 1);
+  const RegOps<EL, NC> R = R0;  // const object: the non-inlined callee cannot legally change it
   double a_rhs[M + 1], a_lhs[M + 1], a_imp[M + 1];
 #pragma unroll
   for (int j = 0; j <= M; ++j) { a_rhs[j] = d.a_rhs[j]; a_lhs[j] = d.a_lhs[j]; a_imp[j] = -d.a_lhs[j]; }
@@ -1364,7 +1394,17 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
     load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n_hi + 1) * cv_stride);
     for (int n = n_hi; n >= n_lo; --n) {
       Vec<EL> w0, rhs;
-#if !QGD_BWD_MERGE_SIDES
+#if QGD_BWD_MERGE_SIDES == 2
+      // implicit side: time level n+1 (its control values are the ones currently loaded), coefficients -a_lhs
+      grad_side_fast<EL, M, NC>(c, R, lam, d.a_lhs, -1.0, w0, hist + slot_sz * (n + 1), true, gKs, gSs);
+      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)(n + 1) * tab_stride, gKs, gSs, gacc);
+      __syncwarp();
+      // explicit side: time level n, coefficients a_rhs; rhs = R(t_n)^T lambda_{n+1}
+      load_cv_fast<EL, M, NC>(c, cvb + (size_t)n * cv_stride);
+      grad_side_fast<EL, M, NC>(c, R, lam, d.a_rhs, 1.0, rhs, hist + slot_sz * n, false, gKs, gSs);
+      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
+      __syncwarp();
+#elif !QGD_BWD_MERGE_SIDES
       {
       double gK[M][NC], gS[M][NC];
       // ---- implicit side: time level n+1 (its control values are the ones currently loaded)
@@ -1389,7 +1429,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       for (int r = 0; r < M; ++r)
 #pragma unroll
         for (int k = 0; k < NC; ++k) { gK[r][k] = 0.0; gS[r][k] = 0.0; }
-      adj_fast<EL, M, NC, true, false>(c, R, lam, a_rhs, rhs, hist + slot_sz * n, gK, gS);  // rhs = R(t_n)^T lambda_{n+1}
+      adj_fast<EL, M, NC, true>(c, R, lam, a_rhs, rhs, hist + slot_sz * n, gK, gS, false);  // rhs = R(t_n)^T lambda_{n+1}
 #pragma unroll
       for (int r = 0; r < M; ++r)
 #pragma unroll
