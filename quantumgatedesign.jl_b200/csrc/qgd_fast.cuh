@@ -51,9 +51,6 @@ namespace qgd {
 #define QGD_QR_LEAN 1
 #endif
 #define QGD_COMPACT_SMEM (QGD_QR_LEAN && QGD_MGS_BLOCK > 1)
-#ifndef QGD_QR_DEPTH
-#define QGD_QR_DEPTH 2  // rows of H / columns of R prefetched ahead of the rotation / back-substitution step
-#endif
 #ifndef QGD_BWD_MERGE_SIDES
 #define QGD_BWD_MERGE_SIDES 0  // gradient sweeps of an adjoint step: 0 two inlined copies, 1 one rolled loop, 2 one real function
 #endif
@@ -913,6 +910,7 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
   const int i0 = 32 * S0;
   if (i0 >= width) return;
   const int iend = min(width, i0 + 32);
+  double loA[CH], loB[CH];
   auto fetch = [&](double (&lo)[CH], int r) {  // row r of the owned columns j = lane + 32 s >= r - 1
 #pragma unroll
     for (int s = S0; s < CH; ++s) {
@@ -939,19 +937,17 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
     if (lane == 0) { dinv[i] = rr; g[i] = cs * gcur; }  // r_ii = cs a + sn b = 1 / rr
     gcur = -sn * gcur;
   };
-  // rows i+1 .. i+D of H are in flight while rotation i is formed: an L2 round trip of these scattered 8-byte loads
-  // (every lane reads its own column) is 800-900 cycles, a rotation 250
-  constexpr int D = QGD_QR_DEPTH;
-  double lo[D][CH];
-#pragma unroll
-  for (int u = 0; u < D; ++u) fetch(lo[u], i0 + 1 + u);
-  for (int i = i0; i < iend; i += D) {
-#pragma unroll
-    for (int u = 0; u < D; ++u) {
-      if (i + u < iend) {
-        rotate(i + u, lo[u]);
-        fetch(lo[u], i + u + 1 + D);
-      }
+  // two rows ahead, hand-unrolled.  Measured: prefetching 1 / 2 / 4 rows ahead gives 382 / 388 / 343
+  // evals/s, a generic depth-D loop at D = 2 gives 377, L1-cached loads 382 -- the kernels are that sensitive to the size
+  // and layout of the per-solve code.
+  fetch(loA, i0 + 1);
+  fetch(loB, i0 + 2);
+  for (int i = i0; i < iend; i += 2) {
+    rotate(i, loA);
+    fetch(loA, i + 3);
+    if (i + 1 < iend) {
+      rotate(i + 1, loB);
+      fetch(loB, i + 4);
     }
   }
 }
@@ -963,6 +959,7 @@ __device__ __forceinline__ void qr_backsub_phase(double (&gi)[CH], const double*
   const int j_lo = 32 * S0;
   if (j_lo >= width) return;
   const int j_hi = min(width, j_lo + 32) - 1;
+  double cA[CH], cB[CH];
   auto fetch = [&](double (&col)[CH], int j) {  // rows i < j of column j
     const double* src = Rg + hoff(max(j, 0));
 #pragma unroll
@@ -979,17 +976,14 @@ __device__ __forceinline__ void qr_backsub_phase(double (&gi)[CH], const double*
       gi[q] = i < j ? fma(-yj, col[q], gi[q]) : (i == j ? yj : gi[q]);
     }
   };
-  constexpr int D = QGD_QR_DEPTH;
-  double col[D][CH];
-#pragma unroll
-  for (int u = 0; u < D; ++u) fetch(col[u], j_hi - u);
-  for (int j = j_hi; j >= j_lo; j -= D) {
-#pragma unroll
-    for (int u = 0; u < D; ++u) {
-      if (j - u >= j_lo) {
-        step(j - u, col[u]);
-        fetch(col[u], j - u - D);
-      }
+  fetch(cA, j_hi);
+  fetch(cB, j_hi - 1);
+  for (int j = j_hi; j >= j_lo; j -= 2) {
+    step(j, cA);
+    fetch(cA, j - 2);
+    if (j - 1 >= j_lo) {
+      step(j - 1, cB);
+      fetch(cB, j - 3);
     }
   }
 }
