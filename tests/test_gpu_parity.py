@@ -428,3 +428,45 @@ def test_estimate_timesteps_per_period(q):
     # order 4: once resolved, every doubling of the steps per period gains about 2^4
     assert len(errs) == 5 and errs[-1] < errs[0] * 1e-3 and errs[-2] / errs[-1] > 8.0, errs
     q.backend.clear_handles()
+
+
+# ---- edge cases of the GMRES driver and of the problem shapes ----------------------------------------------------------
+@pytest.mark.parametrize("name", ["cnot2", "rand_grape", "cnot3_333"])
+def test_gmres_runs_to_maxiter_when_tolerance_is_zero(q, O, name):
+    """abstol = 0: no solve ever meets the tolerance, every GMRES runs its restart = maxiter = 2N iterations, takes the
+    least-squares solution at the cap and stops (IterativeSolvers: done(iteration + 1)); the reference is silent about
+    non-convergence, the iteration counters returned through the ABI equal 2N.  Fast and generic kernels vs the oracle."""
+    prob0, controls, pcof, target, order = _cases(q)[name]
+    prob = prob0.copy()
+    prob.nsteps = 3
+    prob.tf = prob0.tf * 3 / prob0.nsteps
+    prob.gmres_abstol = prob.gmres_reltol = 0.0
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    n2 = prob.real_system_size
+    assert np.all(ref["iters_fwd"] == n2) and np.all(out["iters_fwd"][:, :, 0] == n2)
+    assert np.all(out["iters_adj"][1:, :, 0] == n2)
+    assert rel(out["grad"][:, 0], ref["grad"]) < 1e-8  # 2N Krylov vectors span the space: both are exact up to roundoff
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= 1e-9 * max(abs(ref["infidelity"]), 1e-3)
+    h.close()
+
+
+def test_single_step_single_column_and_order_2(q, O):
+    """Smallest shapes: one time step, one initial-condition column, order 2 (m = 1), one control vector."""
+    prob = q.construct_rand_prob(5, 2, tf=0.3, nsteps=1, gmres_abstol=1e-15, gmres_reltol=1e-15)
+    p1 = q.SchrodingerProb(prob.system_sym, prob.system_asym, prob.sym_operators, prob.asym_operators, prob.u0[:, :1],
+                           prob.v0[:, :1], prob.guard_subspace_projector, prob.tf, 1, prob.N_ess_levels, 1e-15, 1e-15,
+                           prob.preconditioner_type)
+    controls = [q.BSpline2Control(4, p1.tf), q.GRAPEControl(3, p1.tf)]
+    rng = np.random.default_rng(9)
+    pcof = rng.standard_normal(q.get_number_of_control_parameters(controls))
+    target = rng.standard_normal((5, 1)) + 1j * rng.standard_normal((5, 1))
+    for order in (2, 4):
+        h = q.Handle(p1, controls)
+        out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_history=True, want_iters=True)
+        ref = O.discrete_adjoint(p1, controls, pcof, target, order=order)
+        assert rel(out["history"][..., 0], ref["history"]) < RTOL
+        assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+        assert np.array_equal(out["iters_fwd"][:, :, 0], ref["iters_fwd"])
+        h.close()
