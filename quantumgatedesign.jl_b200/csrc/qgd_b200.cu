@@ -274,6 +274,25 @@ void validate_and_load(qgd_handle* h, const qgd_problem_t* p) {
     h->fast_ok = ok;
     h->fast_el = n <= 32 ? 1 : 2;
   }
+  // ---- dense problems whose level count is a multiple of 32: row-major dense copies for the tensor-core path
+  // (qgd_dense.cu); "dense" = more than a quarter of the entries of some operator present
+  if (!h->fast_ok && n % 32 == 0 && n <= 256) {
+    bool dense = false;
+    for (int k = 0; k < L.n_ops; ++k) dense = dense || 4 * L.L[k] > n;
+    if (dense) {
+      const size_t nn = (size_t)n * n;
+      h->dense_ops.assign((size_t)L.n_ops * 2 * nn, 0.0);
+      for (int k = 0; k < L.n_ops; ++k) {
+        const dvec& K = (k == 0) ? h->Ks : Kc[k - 1];
+        const dvec& S = (k == 0) ? h->Ss : Sc[k - 1];
+        for (int r = 0; r < n; ++r)
+          for (int c = 0; c < n; ++c) {  // column-major (r, c) -> row-major
+            h->dense_ops[((size_t)k * 2 + 0) * nn + (size_t)r * n + c] = K[r + (size_t)n * c];
+            h->dense_ops[((size_t)k * 2 + 1) * nn + (size_t)r * n + c] = S[r + (size_t)n * c];
+          }
+      }
+    }
+  }
 
   // ---- upload the static parts
   h->d_u0.reserve((size_t)n * h->nic * 8); h->d_v0.reserve((size_t)n * h->nic * 8);
@@ -656,7 +675,7 @@ int qgd_destroy(qgd_handle_t* h) {
                     &h->d_cvals, &h->d_history, &h->d_final, &h->d_final_all, &h->d_terminal, &h->d_lambda0, &h->d_lamhist,
                     &h->d_gradcol, &h->d_grad, &h->d_guardcol, &h->d_guard, &h->d_infid, &h->d_iters_f, &h->d_iters_a,
                     &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch, &h->d_counter, &h->d_progress, &h->d_carry,
-                    &h->d_theta_op};
+                    &h->d_theta_op, &h->d_dense, &h->d_comb};
   for (DevBuf* b : bufs) b->release();
   if (h->l2_carved) cudaCtxResetPersistingL2Cache();  // hand the persisting L2 lines of the workspace window back
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -1055,9 +1074,18 @@ int qgd_compute_derivatives(qgd_handle_t* h, double* uv, int64_t ncols_in, int32
       }
     CUDA_CHECK(cudaMemcpyAsync(d_cv, cv.data(), cv.size() * 8, cudaMemcpyHostToDevice, h->stream));
     SweepArgs a{};
-    if (!try_derivs_fast(h, d, a, d_uv, (int)ncols_in, d_cv, adjoint)) { QGD_DISPATCH_EL(el, launch_derivs, h, d, a, d_uv, (int)ncols_in, d_cv, adjoint); }
+    reset_stats(h);
+    CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
+    if (!adjoint && dense_derivs_applicable(h, m)) {  // dense operators: FP64 tensor-core contraction (qgd_dense.cu)
+      launch_derivs_dense(h, m, d_uv, (int)ncols_in, d_cv);
+      h->stats.fast_path_launches = -1;  // marks the tensor-core path in the stats of this call
+    } else if (!try_derivs_fast(h, d, a, d_uv, (int)ncols_in, d_cv, adjoint)) {
+      QGD_DISPATCH_EL(el, launch_derivs, h, d, a, d_uv, (int)ncols_in, d_cv, adjoint);
+    }
+    CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
     CUDA_CHECK(cudaMemcpyAsync(uv, d_uv, sz, cudaMemcpyDeviceToHost, h->stream));
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    finish_timing(h, true, false);  // last_forward_ms = device time of the derivative kernel(s)
   });
 }
 

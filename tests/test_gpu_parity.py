@@ -470,3 +470,25 @@ def test_single_step_single_column_and_order_2(q, O):
         assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
         assert np.array_equal(out["iters_fwd"][:, :, 0], ref["iters_fwd"])
         h.close()
+
+
+# ---- FP64 tensor-core (DMMA) form of the Taylor recursion for dense operators (qgd_dense.cu) -------------------------
+@pytest.mark.parametrize("N,order,ncols", [(32, 10, 13), (64, 8, 8), (64, 2, 3), (256, 10, 5)])
+def test_dense_tensor_core_derivatives_vs_oracle(q, O, N, order, ncols):
+    """compute_derivatives! (src/hermite.jl:56-101) for dense operators as a [2N x 2N] x [2N x columns] contraction on
+    the FP64 tensor cores: all Taylor columns vs the oracle (summation order differs: 1e-12), ragged column counts."""
+    prob, controls, pcof, target, _ = q.configs.dense_random(N=N, nic=2, Nc=3, nsteps=2, order=order, gmres_tol=1e-13)
+    h = q.Handle(prob, controls)
+    m = order // 2
+    rng = np.random.default_rng(4)
+    cre = rng.standard_normal((m + 1, prob.N_operators))
+    cim = rng.standard_normal((m + 1, prob.N_operators))
+    uv = np.zeros((prob.real_system_size, m + 1, ncols), order="F")
+    uv[:, 0, :] = rng.standard_normal((prob.real_system_size, ncols))
+    out = h.compute_derivatives(uv, order, cre, cim, adjoint=False)
+    assert h.stats()["fast_path_launches"] == -1, "the dense problem did not take the tensor-core path"
+    for c in range(ncols):
+        ref = O.compute_derivatives(prob, controls, uv[:, :, c], order, cre, cim, adjoint=False)
+        for j in range(m + 1):
+            assert rel(out[:, j, c], ref[:, j]) < 1e-12, (c, j)
+    h.close()
