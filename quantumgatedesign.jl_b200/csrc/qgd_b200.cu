@@ -1076,8 +1076,8 @@ int qgd_compute_derivatives(qgd_handle_t* h, double* uv, int64_t ncols_in, int32
     SweepArgs a{};
     reset_stats(h);
     CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
-    if (!adjoint && dense_derivs_applicable(h, m)) {  // dense operators: FP64 tensor-core contraction (qgd_dense.cu)
-      launch_derivs_dense(h, m, d_uv, (int)ncols_in, d_cv);
+    if (dense_derivs_applicable(h, m)) {  // dense operators: FP64 tensor-core contraction (qgd_dense.cu)
+      launch_derivs_dense(h, m, d_uv, (int)ncols_in, d_cv, adjoint);
       h->stats.fast_path_launches = -1;  // marks the tensor-core path in the stats of this call
     } else if (!try_derivs_fast(h, d, a, d_uv, (int)ncols_in, d_cv, adjoint)) {
       QGD_DISPATCH_EL(el, launch_derivs, h, d, a, d_uv, (int)ncols_in, d_cv, adjoint);

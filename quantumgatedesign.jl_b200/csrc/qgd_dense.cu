@@ -38,6 +38,30 @@ __global__ void k_dense_combine(const double* __restrict__ ops /*[Nc+1][2][N][N]
   }
 }
 
+// One Taylor pair: (aU, aV) += A_d B for the 32 level rows of this warp, B = a [2N x 8] block in shared memory
+// ([column][S] layout), A_d = [S_d K_d; -K_d S_d] streamed from L2.
+__device__ __forceinline__ void dense_pair(const double* __restrict__ comb, int d, int N, int r0, int lane, const double* B, int S,
+                                           double (&aU)[4][2], double (&aV)[4][2]) {
+  const int ar = lane >> 2, ak = lane & 3;
+  const size_t nn = (size_t)N * N;
+  const double* Kd = comb + ((size_t)d * 2 + 0) * nn + (size_t)(r0 + ar) * N + ak;
+  const double* Sd = comb + ((size_t)d * 2 + 1) * nn + (size_t)(r0 + ar) * N + ak;
+  const double* Bu = B + (size_t)ar * S + ak;
+  const double* Bv = Bu + N;
+#pragma unroll 4
+  for (int k0 = 0; k0 < N; k0 += 4) {
+    const double bu = Bu[k0], bv = Bv[k0], nbu = -bu;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const double aS = __ldg(Sd + (size_t)8 * t * N + k0), aK = __ldg(Kd + (size_t)8 * t * N + k0);
+      dmma884_acc(aU[t][0], aU[t][1], aS, bu);
+      dmma884_acc(aU[t][0], aU[t][1], aK, bv);
+      dmma884_acc(aV[t][0], aV[t][1], aS, bv);
+      dmma884_acc(aV[t][0], aV[t][1], aK, nbu);
+    }
+  }
+}
+
 // uv: [2N][1+M][ncols], column 0 of every state column given; columns 1..M are written.
 template <int M>
 __global__ void __launch_bounds__(256, 1) k_derivs_dense(const double* __restrict__ comb, int N, double* uv, int ncols) {
@@ -45,7 +69,6 @@ __global__ void __launch_bounds__(256, 1) k_derivs_dense(const double* __restric
   const int N2 = 2 * N, S = N2 + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 8;
-  const size_t nn = (size_t)N * N;
   // Taylor column 0 of the 8 state columns (zeros beyond ncols)
   for (int idx = threadIdx.x; idx < 8 * N2; idx += blockDim.x) {
     const int col = idx / N2, row = idx % N2;
@@ -61,23 +84,7 @@ __global__ void __launch_bounds__(256, 1) k_derivs_dense(const double* __restric
     for (int t = 0; t < 4; ++t) { aU[t][0] = aU[t][1] = aV[t][0] = aV[t][1] = 0.0; }
 #pragma unroll 1
     for (int i = 0; i <= j; ++i) {
-      const int d = j - i;
-      const double* Kd = comb + ((size_t)d * 2 + 0) * nn + (size_t)(r0 + ar) * N + ak;
-      const double* Sd = comb + ((size_t)d * 2 + 1) * nn + (size_t)(r0 + ar) * N + ak;
-      const double* Wu = Wt + ((size_t)i * 8 + ar) * S + ak;  // B[k = ak][n = ar] = W_i[k0 + ak][column ar]
-      const double* Wv = Wu + N;
-#pragma unroll 4
-      for (int k0 = 0; k0 < N; k0 += 4) {
-        const double bu = Wu[k0], bv = Wv[k0], nbu = -bu;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const double aS = __ldg(Sd + (size_t)8 * t * N + k0), aK = __ldg(Kd + (size_t)8 * t * N + k0);
-          dmma884_acc(aU[t][0], aU[t][1], aS, bu);   // u' += S u + K v
-          dmma884_acc(aU[t][0], aU[t][1], aK, bv);
-          dmma884_acc(aV[t][0], aV[t][1], aS, bv);   // v' += S v - K u
-          dmma884_acc(aV[t][0], aV[t][1], aK, nbu);
-        }
-      }
+      dense_pair(comb, j - i, N, r0, lane, Wt + (size_t)i * 8 * S, S, aU, aV);  // W_i is the B operand
     }
     // D fragment: row ar, columns 2 ak, 2 ak + 1
     const double inv = 1.0 / (double)(j + 1);
@@ -98,15 +105,68 @@ __global__ void __launch_bounds__(256, 1) k_derivs_dense(const double* __restric
   }
 }
 
+// Adjoint columns Lambda_jt = W_jt(t)^T x, jt = 1..M (compute_adjoint_derivatives!, reference src/hermite.jl:284-305), each
+// by the O(m^2) reverse sweep  what_j = [j = jt] x;  for j = jt-1..0: what_{j-d} -= (1/(j+1)) A_d what_{j+1}, d = 0..j
+// (K symmetric, S antisymmetric: A_d^T = -A_d), as the same tensor-core contraction.
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_derivs_dense_adj(const double* __restrict__ comb, int N, double* uv, int ncols) {
+  extern __shared__ __align__(16) double Wt[];  // what[(M+1)][8][S]
+  const int N2 = 2 * N, S = N2 + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 8;
+  const int r0 = 32 * warp, ar = lane >> 2, ak = lane & 3;
+#pragma unroll 1
+  for (int jt = 1; jt <= M; ++jt) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (jt + 1) * 8 * N2; idx += blockDim.x) {
+      const int row = idx % N2, col = (idx / N2) % 8, jj = idx / (8 * N2);
+      Wt[((size_t)jj * 8 + col) * S + row] =
+          (jj == jt && c0 + col < ncols) ? uv[(size_t)row + (size_t)N2 * (M + 1) * (c0 + col)] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = jt - 1; j >= 0; --j) {
+      const double inv = 1.0 / (double)(j + 1);
+      const double* Y = Wt + (size_t)(j + 1) * 8 * S;
+#pragma unroll 1
+      for (int dd = 0; dd <= j; ++dd) {
+        double aU[4][2], aV[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { aU[t][0] = aU[t][1] = aV[t][0] = aV[t][1] = 0.0; }
+        dense_pair(comb, dd, N, r0, lane, Y, S, aU, aV);
+        double* Wn = Wt + (size_t)(j - dd) * 8 * S;  // own rows only: no other warp touches them in this stage
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int row = r0 + 8 * t + ar;
+          Wn[(size_t)(2 * ak) * S + row] -= aU[t][0] * inv;
+          Wn[(size_t)(2 * ak + 1) * S + row] -= aU[t][1] * inv;
+          Wn[(size_t)(2 * ak) * S + N + row] -= aV[t][0] * inv;
+          Wn[(size_t)(2 * ak + 1) * S + N + row] -= aV[t][1] * inv;
+        }
+      }
+      __syncthreads();  // what_j is complete: it is the B operand of the next stage
+    }
+    for (int idx = threadIdx.x; idx < 8 * N2; idx += blockDim.x) {
+      const int row = idx % N2, col = idx / N2;
+      if (c0 + col < ncols) uv[(size_t)row + (size_t)N2 * (jt + (size_t)(M + 1) * (c0 + col))] = Wt[(size_t)col * S + row];
+    }
+  }
+}
+
 }  // namespace qgd
 
 namespace {
 template <int M>
-void launch_dense_t(qgd_handle* h, const double* comb, double* uv, int ncols) {
+void launch_dense_t(qgd_handle* h, const double* comb, double* uv, int ncols, int adjoint) {
   const int N = h->N, S = 2 * N + 4;
   const size_t smem = (size_t)(M + 1) * 8 * S * 8;
-  CUDA_CHECK(cudaFuncSetAttribute(qgd::k_derivs_dense<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  qgd::k_derivs_dense<M><<<(ncols + 7) / 8, 32 * (N / 32), smem, h->stream>>>(comb, N, uv, ncols);
+  if (adjoint) {
+    CUDA_CHECK(cudaFuncSetAttribute(qgd::k_derivs_dense_adj<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qgd::k_derivs_dense_adj<M><<<(ncols + 7) / 8, 32 * (N / 32), smem, h->stream>>>(comb, N, uv, ncols);
+  } else {
+    CUDA_CHECK(cudaFuncSetAttribute(qgd::k_derivs_dense<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qgd::k_derivs_dense<M><<<(ncols + 7) / 8, 32 * (N / 32), smem, h->stream>>>(comb, N, uv, ncols);
+  }
   CUDA_CHECK(cudaGetLastError());
   h->stats.kernel_launches++;
 }
@@ -120,8 +180,8 @@ bool dense_derivs_applicable(const qgd_handle* h, int m) {
   return (size_t)(m + 1) * 8 * (2 * h->N + 4) * 8 <= h->prop.sharedMemPerBlockOptin;
 }
 
-// d_uv [2N][1+m][ncols] and d_cv [2][m+1][Nc] on the device; forward recursion only.
-void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const double* d_cv) {
+// d_uv [2N][1+m][ncols] and d_cv [2][m+1][Nc] on the device; adjoint != 0: the columns Lambda_j = W_j^T x.
+void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const double* d_cv, int adjoint) {
   const int N = h->N;
   const size_t nn = (size_t)N * N;
   if (h->d_dense.cap == 0) {  // dense row-major copies of the operators, uploaded on first use
@@ -136,11 +196,11 @@ void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const do
   h->stats.kernel_launches++;
   const double* comb = h->d_comb.as<double>();
   switch (m) {
-    case 1: launch_dense_t<1>(h, comb, d_uv, ncols); break;
-    case 2: launch_dense_t<2>(h, comb, d_uv, ncols); break;
-    case 3: launch_dense_t<3>(h, comb, d_uv, ncols); break;
-    case 4: launch_dense_t<4>(h, comb, d_uv, ncols); break;
-    case 5: launch_dense_t<5>(h, comb, d_uv, ncols); break;
-    default: launch_dense_t<6>(h, comb, d_uv, ncols); break;
+    case 1: launch_dense_t<1>(h, comb, d_uv, ncols, adjoint); break;
+    case 2: launch_dense_t<2>(h, comb, d_uv, ncols, adjoint); break;
+    case 3: launch_dense_t<3>(h, comb, d_uv, ncols, adjoint); break;
+    case 4: launch_dense_t<4>(h, comb, d_uv, ncols, adjoint); break;
+    case 5: launch_dense_t<5>(h, comb, d_uv, ncols, adjoint); break;
+    default: launch_dense_t<6>(h, comb, d_uv, ncols, adjoint); break;
   }
 }

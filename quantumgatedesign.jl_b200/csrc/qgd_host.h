@@ -117,4 +117,4 @@ QGD_DECLARE_FAST_LAUNCHERS(6)
 
 // FP64 tensor-core Taylor recursion for dense operators (qgd_dense.cu)
 bool dense_derivs_applicable(const qgd_handle* h, int m);
-void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const double* d_cv);
+void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const double* d_cv, int adjoint);

@@ -485,10 +485,11 @@ def test_dense_tensor_core_derivatives_vs_oracle(q, O, N, order, ncols):
     cim = rng.standard_normal((m + 1, prob.N_operators))
     uv = np.zeros((prob.real_system_size, m + 1, ncols), order="F")
     uv[:, 0, :] = rng.standard_normal((prob.real_system_size, ncols))
-    out = h.compute_derivatives(uv, order, cre, cim, adjoint=False)
-    assert h.stats()["fast_path_launches"] == -1, "the dense problem did not take the tensor-core path"
-    for c in range(ncols):
-        ref = O.compute_derivatives(prob, controls, uv[:, :, c], order, cre, cim, adjoint=False)
-        for j in range(m + 1):
-            assert rel(out[:, j, c], ref[:, j]) < 1e-12, (c, j)
+    for adjoint in (False, True):  # forward Taylor columns; adjoint columns W_j^T x (reverse sweep, A_d^T = -A_d)
+        out = h.compute_derivatives(uv, order, cre, cim, adjoint=adjoint)
+        assert h.stats()["fast_path_launches"] == -1, "the dense problem did not take the tensor-core path"
+        for c in range(ncols if not adjoint else min(ncols, 3)):  # the oracle's adjoint recursion is exponential in m
+            ref = O.compute_derivatives(prob, controls, uv[:, :, c], order, cre, cim, adjoint=adjoint)
+            for j in range(m + 1):
+                assert rel(out[:, j, c], ref[:, j]) < 1e-12, (adjoint, c, j)
     h.close()
