@@ -524,7 +524,7 @@ void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t 
   if (want_iters) { h->d_iters_f.reserve((size_t)h->nsteps * h->ncol * B * 4); a.iters = h->d_iters_f.as<int>(); }
   a.forcing_in = d_forcing;
   CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
-  if (d_forcing || !try_forward_fast(h, d, a)) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
+  if (d_forcing || !(try_forward_fast(h, d, a) || try_forward_dense(h, d, a))) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
   CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
   h->hist_B = B; h->hist_order = order; h->hist_nsteps = h->nsteps; h->hist_save = save_every; h->hist_valid = d_forcing == nullptr;
 }
@@ -675,7 +675,7 @@ int qgd_destroy(qgd_handle_t* h) {
                     &h->d_cvals, &h->d_history, &h->d_final, &h->d_final_all, &h->d_terminal, &h->d_lambda0, &h->d_lamhist,
                     &h->d_gradcol, &h->d_grad, &h->d_guardcol, &h->d_guard, &h->d_infid, &h->d_iters_f, &h->d_iters_a,
                     &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch, &h->d_counter, &h->d_progress, &h->d_carry,
-                    &h->d_theta_op, &h->d_dense, &h->d_comb};
+                    &h->d_theta_op, &h->d_dense, &h->d_comb, &h->d_dense_ws};
   for (DevBuf* b : bufs) b->release();
   if (h->l2_carved) cudaCtxResetPersistingL2Cache();  // hand the persisting L2 lines of the workspace window back
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);

@@ -16,6 +16,7 @@
 // This is the building block of the dense (C4) sweep: the generic sweep kernels reach 0.4 TFLOP/s on that shape
 // (profiles/r01_c4_generic.json); qgd_compute_derivatives routes dense problems with N a multiple of 32 here.
 #include "qgd_host.h"
+#include "qgd_kernels.cuh"
 
 #include <cstdlib>
 
@@ -62,20 +63,13 @@ __device__ __forceinline__ void dense_pair(const double* __restrict__ comb, int 
   }
 }
 
-// uv: [2N][1+M][ncols], column 0 of every state column given; columns 1..M are written.
+// The Taylor recursion of one time level on the 8 state columns of a CTA: Wt[0] (the [column][S] tile of W_0) is
+// filled and visible (barrier done by the caller); fills Wt[1..M]; ends with a CTA barrier.  Warp w owns the level
+// rows [32 w, 32 w + 32) of the u and the v block; blockDim.x = N.
 template <int M>
-__global__ void __launch_bounds__(256, 1) k_derivs_dense(const double* __restrict__ comb, int N, double* uv, int ncols) {
-  extern __shared__ __align__(16) double Wt[];  // [(M+1)][8][S]
-  const int N2 = 2 * N, S = N2 + 4;
+__device__ __forceinline__ void dense_recursion(const double* __restrict__ comb, int N, double* Wt, int S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 8;
-  // Taylor column 0 of the 8 state columns (zeros beyond ncols)
-  for (int idx = threadIdx.x; idx < 8 * N2; idx += blockDim.x) {
-    const int col = idx / N2, row = idx % N2;
-    Wt[(size_t)col * S + row] = (c0 + col < ncols) ? uv[(size_t)row + (size_t)N2 * (M + 1) * (c0 + col)] : 0.0;
-  }
-  __syncthreads();
-  const int r0 = 32 * warp;           // level rows of this warp
+  const int r0 = 32 * warp;                 // level rows of this warp
   const int ar = lane >> 2, ak = lane & 3;  // A fragment: row ar, k index ak;  B fragment: k index ak, column ar
 #pragma unroll 1
   for (int j = 0; j < M; ++j) {
@@ -99,6 +93,21 @@ __global__ void __launch_bounds__(256, 1) k_derivs_dense(const double* __restric
     }
     __syncthreads();
   }
+}
+
+// uv: [2N][1+M][ncols], column 0 of every state column given; columns 1..M are written.
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_derivs_dense(const double* __restrict__ comb, int N, double* uv, int ncols) {
+  extern __shared__ __align__(16) double Wt[];  // [(M+1)][8][S]
+  const int N2 = 2 * N, S = N2 + 4;
+  const int c0 = blockIdx.x * 8;
+  // Taylor column 0 of the 8 state columns (zeros beyond ncols)
+  for (int idx = threadIdx.x; idx < 8 * N2; idx += blockDim.x) {
+    const int col = idx / N2, row = idx % N2;
+    Wt[(size_t)col * S + row] = (c0 + col < ncols) ? uv[(size_t)row + (size_t)N2 * (M + 1) * (c0 + col)] : 0.0;
+  }
+  __syncthreads();
+  dense_recursion<M>(comb, N, Wt, S);
   for (int idx = threadIdx.x; idx < M * 8 * N2; idx += blockDim.x) {
     const int row = idx % N2, col = (idx / N2) % 8, jj = 1 + idx / (8 * N2);
     if (c0 + col < ncols) uv[(size_t)row + (size_t)N2 * (jj + (size_t)(M + 1) * (c0 + col))] = Wt[((size_t)jj * 8 + col) * S + row];
@@ -153,6 +162,231 @@ __global__ void __launch_bounds__(256, 1) k_derivs_dense_adj(const double* __res
   }
 }
 
+
+// ---- the dense forward sweep ----------------------------------------------------------------------------------
+// eval_forward! (reference src/forward_evolution.jl:88-245) for dense Hamiltonians: one CTA marches 8 initial-condition
+// columns of one control vector through all time steps in lockstep.  Every operator application -- the explicit
+// Taylor columns at t_n and each GMRES matvec with LHS(t_{n+1}) (LHSHolder, :583-592) -- is the CTA-wide tensor-core
+// contraction [2N x 2N] x [2N x 8] above with the pre-combined operators of that time level (k_dense_combine_levels);
+// the per-column vector work of GMRES (IterativeSolvers gmres_iterable!, SURVEY App. B: modified Gram-Schmidt with
+// warp-shuffle dot products, null-vector residual recurrence, Givens least squares) stays per warp, one warp per
+// column, exactly as in gmres_warp (qgd_warp.cuh).  The columns of a CTA are a small state machine each (initial /
+// restart residual, Arnoldi step, done): a column that has converged idles through the remaining contractions of the
+// step.  Krylov basis, Hessenberg matrix, x and b live in global memory (L2); the work vector w lives in the W_1 tile.
+struct DenseSweepArgs {
+  const double* comb;  // [B][nsteps+1][M][2][N][N]
+  double* xs;          // [grid][8][2N]  state / GMRES iterate
+  double* bs;          // [grid][8][2N]  right-hand side
+  double* aux;         // [grid][8][3][2N+2]  Hessenberg column, null vector, least-squares rhs
+};
+
+__global__ void k_dense_combine_levels(const double* __restrict__ ops, int N, int Nc, int m, const double* __restrict__ cvals /*[levels][2][m+1][Nc]*/,
+                                       double* __restrict__ comb /*[levels][m][2][N][N]*/) {
+  const size_t nn = (size_t)N * N;
+  const size_t total = (size_t)m * 2 * nn;
+  const double* cv = cvals + (size_t)blockIdx.y * 2 * (m + 1) * Nc;
+  double* out = comb + (size_t)blockIdx.y * total;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = idx % nn;
+    const int ks = (int)((idx / nn) % 2), d = (int)(idx / (2 * nn));
+    double s = d == 0 ? ops[(size_t)ks * nn + e] : 0.0;
+    for (int k = 0; k < Nc; ++k) s = fma(cv[((size_t)ks * (m + 1) + d) * Nc + k], ops[((size_t)(k + 1) * 2 + ks) * nn + e], s);
+    out[idx] = s;
+  }
+}
+
+enum { DCOL_DONE = 0, DCOL_RESID0 = 1, DCOL_RESID = 2, DCOL_ARNOLDI = 3 };
+
+__device__ __forceinline__ double dense_dot(const double* a, const double* b, int N2, int lane) {
+  double s = 0.0;
+  for (int r = lane; r < N2; r += 32) s = fma(a[r], b[r], s);
+  return warp_sum(s);
+}
+
+// DiagonalHamiltonianPreconditioner (src/preconditioners.jl:108-126) on a vector in shared memory
+__device__ __forceinline__ void dense_precond(const QgdDevProb& d, double* w, int lane) {
+  if (d.precond != QGD_PRECOND_DIAGONAL) return;
+  const int N = d.N;
+  const double* pd = reinterpret_cast<const double*>(d.blob + d.lay.off_pre[0]);
+  const double* dg = pd; const double* up = pd + d.N2; const double* ratio = up + N; const double* den = ratio + N;
+  for (int r = lane; r < N; r += 32) {
+    double xv = w[N + r] - w[r] * ratio[r];
+    xv = xv / den[r];
+    double xu = w[r] - up[r] * xv;
+    xu = xu / dg[r];
+    w[r] = xu; w[N + r] = xv;
+  }
+  __syncwarp();
+}
+
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_forward_dense(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
+                                                           const __grid_constant__ DenseSweepArgs ds) {
+  extern __shared__ __align__(16) double Wt[];  // [(M+1)][8][S]
+  __shared__ int s_state[8], s_k[8], s_it[8];
+  __shared__ double s_beta[8], s_cur[8], s_resb[8], s_acc[8];
+  const int N = d.N, N2 = d.N2, S = N2 + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int groups = (d.ncol + 7) / 8;
+  const int items = a.B * groups;
+  const size_t nn = (size_t)N * N, lvl = (size_t)M * 2 * nn;
+  const size_t slot_sz = (size_t)N2 * (M + 1);
+  const int restart = N2, maxiter = N2;
+  const double tol = d.abstol;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / groups, c0 = (item % groups) * 8;
+    const double* comb_b = ds.comb + (size_t)b * (d.nsteps + 1) * lvl;
+    for (int col = warp; col < 8; col += nwarps) {
+      const int cl = c0 + col;
+      double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+      for (int r = lane; r < N; r += 32) {
+        X[r] = cl < d.ncol ? d.u0[r + (size_t)N * (d.col0 + cl)] : 0.0;
+        X[N + r] = cl < d.ncol ? d.v0[r + (size_t)N * (d.col0 + cl)] : 0.0;
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int n = 0; n <= d.nsteps; ++n) {
+      // ---- explicit side: Taylor columns of x at t_n, history slot, right-hand side and initial guess
+      for (int col = warp; col < 8; col += nwarps) {
+        const double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+        for (int r = lane; r < N2; r += 32) Wt[(size_t)col * S + r] = X[r];
+      }
+      __syncthreads();
+      dense_recursion<M>(comb_b + (size_t)n * lvl, N, Wt, S);
+      for (int col = warp; col < 8; col += nwarps) {
+        const int cl = c0 + col;
+        const bool valid = cl < d.ncol;
+        double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+        double* Bv = ds.bs + ((size_t)blockIdx.x * 8 + col) * N2;
+        double* slot = nullptr;
+        if (valid && a.history && n % a.save_every == 0)
+          slot = a.history + slot_sz * ((size_t)(n / a.save_every) + (size_t)a.nslots * ((size_t)cl + (size_t)d.ncol * b));
+        for (int r = lane; r < N2; r += 32) {
+          const double w0 = Wt[(size_t)col * S + r];
+          double rhs = w0 * d.a_rhs[0], guess = w0;
+          if (slot) __stcs(slot + r, w0);
+#pragma unroll
+          for (int j = 1; j <= M; ++j) {
+            const double wj = Wt[((size_t)j * 8 + col) * S + r];
+            rhs = fma(d.a_rhs[j], wj, rhs);
+            guess = fma(d.a_tay[j], wj, guess);
+            if (slot) __stcs(slot + (size_t)j * N2 + r, wj);
+          }
+          if (n < d.nsteps) {
+            Bv[r] = rhs; X[r] = guess;
+            Wt[(size_t)col * S + r] = guess;  // x0 = Taylor expansion: the first contraction forms the initial residual
+          } else if (valid) {
+            a.final_state[(size_t)r + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b)] = w0;
+          }
+        }
+        if (lane == 0) { s_state[col] = valid ? DCOL_RESID0 : DCOL_DONE; s_it[col] = 0; s_k[col] = 1; }
+      }
+      if (n == d.nsteps) { __syncthreads(); break; }
+      __syncthreads();
+      // ---- implicit side: LHS(t_{n+1}) x = rhs by GMRES, the 8 columns in lockstep
+      const double* comb1 = comb_b + (size_t)(n + 1) * lvl;
+#pragma unroll 1
+      while (true) {
+        dense_recursion<M>(comb1, N, Wt, S);
+        for (int col = warp; col < 8; col += nwarps) {
+          const int st = s_state[col];
+          if (st == DCOL_DONE) continue;
+          const size_t ws_slot = (size_t)blockIdx.x * 8 + col;
+          double* X = ds.xs + ws_slot * N2;
+          const double* Bv = ds.bs + ws_slot * N2;
+          double* Vg = a.Vws + ws_slot * a.v_stride;
+          double* hcol = ds.aux + ws_slot * 3 * (N2 + 2);
+          double* nullv = hcol + (N2 + 2);
+          WarpCtx c;
+          c.d = &d; c.lane = lane; c.Hg = a.Hws + ws_slot * a.h_stride; c.yv = nullv + (N2 + 2);
+          double* xin = Wt + (size_t)col * S;        // operand of the next contraction
+          double* ws = Wt + (size_t)(8 + col) * S;   // work vector w (the W_1 tile of this column)
+          for (int r = lane; r < N2; r += 32) {      // out = sum_j c_j (-dt)^j W_j  (build_LHS!, src/hermite.jl:435-457)
+            double o = xin[r] * d.a_lhs[0];
+#pragma unroll
+            for (int j = 1; j <= M; ++j) o = fma(d.a_lhs[j], Wt[((size_t)j * 8 + col) * S + r], o);
+            ws[r] = o;
+          }
+          __syncwarp();
+          int k = s_k[col], it = s_it[col], nst = DCOL_ARNOLDI;
+          double beta = s_beta[col], cur = s_cur[col], resb = s_resb[col], acc = s_acc[col];
+          if (st != DCOL_ARNOLDI) {  // residual of the initial guess / of a restart: v_1 = Pl^-1 (b - A x) / beta
+            for (int r = lane; r < N2; r += 32) ws[r] = Bv[r] - ws[r];
+            __syncwarp();
+            dense_precond(d, ws, lane);
+            beta = sqrt(dense_dot(ws, ws, N2, lane));
+            const double inv = 1.0 / beta;
+            for (int r = lane; r < N2; r += 32) { const double v = ws[r] * inv; Vg[r] = v; xin[r] = v; }
+            if (st == DCOL_RESID0) cur = beta;  // a restart keeps residual.current, as the package does
+            resb = beta; acc = 1.0; k = 1;
+            if (lane == 0) nullv[0] = 1.0;
+            if (st == DCOL_RESID0 && !(cur > tol)) nst = DCOL_DONE;
+          } else {  // one Arnoldi step: expand!, orthogonalize_and_normalize!, update_residual!
+            dense_precond(d, ws, lane);
+            double dsum = 0.0;
+            for (int i = 0; i < k; ++i) {
+              const double* vi = Vg + (size_t)i * N2;
+              const double hh = dense_dot(vi, ws, N2, lane);
+              if (lane == 0) hcol[i] = hh;
+              for (int r = lane; r < N2; r += 32) ws[r] = fma(-hh, vi[r], ws[r]);
+              dsum += nullv[i] * hh;
+            }
+            const double nrm = sqrt(dense_dot(ws, ws, N2, lane));
+            const double inv = 1.0 / nrm;
+            for (int r = lane; r < N2; r += 32) { const double v = ws[r] * inv; Vg[(size_t)k * N2 + r] = v; xin[r] = v; }
+            const double nv = -(dsum / nrm);
+            if (lane == 0) { hcol[k] = nrm; nullv[k] = nv; }
+            acc += nv * nv;
+            cur = resb / sqrt(acc);
+            __syncwarp();
+            {
+              double* Hc = c.Hg + hoff(k - 1);
+              for (int i = lane; i <= k; i += 32) Hc[i] = hcol[i];
+            }
+            k += 1; it += 1;
+            if (k == restart + 1 || !(cur > tol)) {
+              const int width = k - 1;
+              __syncwarp();
+              solve_least_squares(c, width, beta);
+              for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 1:k-1] y
+                const double yj = c.yv[j];
+                const double* vj = Vg + (size_t)j * N2;
+                for (int r = lane; r < N2; r += 32) X[r] = fma(yj, vj[r], X[r]);
+              }
+              k = 1;
+              if (cur > tol && it < maxiter) {
+                nst = DCOL_RESID;
+                for (int r = lane; r < N2; r += 32) xin[r] = X[r];
+              } else {
+                nst = DCOL_DONE;
+              }
+            } else if (it >= maxiter) {
+              nst = DCOL_DONE;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+            s_state[col] = nst; s_k[col] = k; s_it[col] = it;
+            s_beta[col] = beta; s_cur[col] = cur; s_resb[col] = resb; s_acc[col] = acc;
+          }
+        }
+        __syncthreads();
+        int any = 0;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) any |= s_state[cc];
+        if (!any) break;
+      }
+      if (a.iters)
+        for (int col = warp; col < 8; col += nwarps)
+          if (lane == 0 && c0 + col < d.ncol)
+            a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)(c0 + col) + (size_t)d.ncol * b)] = s_it[col];
+      // the barrier after the next explicit-side fill orders these reads before the next writes of s_it
+    }
+  }
+}
+
 }  // namespace qgd
 
 namespace {
@@ -203,4 +437,69 @@ void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const do
     case 5: launch_dense_t<5>(h, comb, d_uv, ncols, adjoint); break;
     default: launch_dense_t<6>(h, comb, d_uv, ncols, adjoint); break;
   }
+}
+
+namespace {
+template <int M>
+void launch_forward_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs a, qgd::DenseSweepArgs ds, int grid, size_t smem) {
+  CUDA_CHECK(cudaFuncSetAttribute(qgd::k_forward_dense<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  qgd::k_forward_dense<M><<<grid, d.N, smem, h->stream>>>(d, a, ds);
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+}
+}  // namespace
+
+// Forward sweep of a dense problem on the tensor-core contraction (k_forward_dense).  false: not applicable (sparse or
+// register-operator problem, LU preconditioner, level count not a multiple of 32, the per-level operators of the whole
+// time grid do not fit the device memory) -- the caller then uses the generic kernels.
+bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a_in) {
+  const int m = d.m, N = h->N, N2 = h->N2;
+  if (getenv("QGD_DISABLE_DENSE_SWEEP")) return false;
+  if (!dense_derivs_applicable(h, m) || h->precond == QGD_PRECOND_LU || h->Nc < 1) return false;
+  const size_t smem = (size_t)(m + 1) * 8 * (N2 + 4) * 8;
+  if (smem + 512 > h->prop.sharedMemPerBlockOptin) return false;
+  if ((size_t)a_in.B * (h->nsteps + 1) > 65535) return false;  // grid.y of the operator combination
+  const size_t nn = (size_t)N * N, levels = (size_t)a_in.B * (h->nsteps + 1);
+  const size_t comb_bytes = levels * m * 2 * nn * 8;
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  if (comb_bytes > h->d_comb.cap && comb_bytes > (free_b / 10) * 7) return false;
+  qgd::SweepArgs a = a_in;
+  if (h->d_dense.cap == 0) {
+    h->d_dense.reserve(h->dense_ops.size() * 8);
+    CUDA_CHECK(cudaMemcpyAsync(h->d_dense.p, h->dense_ops.data(), h->dense_ops.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->d_comb.reserve(comb_bytes);
+  {
+    const size_t total = (size_t)m * 2 * nn;
+    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 1024), (unsigned)levels);
+    qgd::k_dense_combine_levels<<<grid, 256, 0, h->stream>>>(h->d_dense.as<double>(), N, h->Nc, m, a.cvals, h->d_comb.as<double>());
+    CUDA_CHECK(cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+  const int groups = (h->ncol + 7) / 8;
+  const int grid = std::max(1, std::min(a.B * groups, h->prop.multiProcessorCount));
+  const size_t slots = (size_t)grid * 8;
+  a.v_stride = (size_t)(N2 + 1) * N2;
+  a.h_stride = (size_t)N2 * (N2 + 3) / 2 + 2;
+  h->d_V.reserve(slots * a.v_stride * 8);
+  h->d_H.reserve(slots * a.h_stride * 8);
+  a.Vws = h->d_V.as<double>();
+  a.Hws = h->d_H.as<double>();
+  h->d_dense_ws.reserve(slots * (2 * (size_t)N2 + 3 * ((size_t)N2 + 2)) * 8);
+  qgd::DenseSweepArgs ds{};
+  ds.comb = h->d_comb.as<double>();
+  ds.xs = h->d_dense_ws.as<double>();
+  ds.bs = ds.xs + slots * N2;
+  ds.aux = ds.bs + slots * N2;
+  switch (m) {
+    case 1: launch_forward_dense_t<1>(h, d, a, ds, grid, smem); break;
+    case 2: launch_forward_dense_t<2>(h, d, a, ds, grid, smem); break;
+    case 3: launch_forward_dense_t<3>(h, d, a, ds, grid, smem); break;
+    case 4: launch_forward_dense_t<4>(h, d, a, ds, grid, smem); break;
+    case 5: launch_forward_dense_t<5>(h, d, a, ds, grid, smem); break;
+    default: launch_forward_dense_t<6>(h, d, a, ds, grid, smem); break;
+  }
+  h->stats.fast_path_launches++;
+  return true;
 }

@@ -77,7 +77,7 @@ struct qgd_handle {
   int fast_el = 0;
   // dense tensor-core path (qgd_dense.cu): row-major dense copies of the operators [(Nc+1)][2][N][N] (operator 0 = drift)
   std::vector<double> dense_ops;
-  DevBuf d_dense, d_comb;
+  DevBuf d_dense, d_comb, d_dense_ws;
   bool host_controls = false;     // some control is QGD_CONTROL_HOST_TABLE: only the qgd_*_tables entry points work
   bool tables_from_host = false;  // inside a qgd_*_tables call: d_cvals / d_table hold the caller's tables
   bool l2_carved = false;  // cudaLimitPersistingL2CacheSize set for the workspace window (qgd_fast_inst.cuh)
@@ -118,3 +118,4 @@ QGD_DECLARE_FAST_LAUNCHERS(6)
 // FP64 tensor-core Taylor recursion for dense operators (qgd_dense.cu)
 bool dense_derivs_applicable(const qgd_handle* h, int m);
 void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const double* d_cv, int adjoint);
+bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a);

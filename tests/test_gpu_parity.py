@@ -2,6 +2,8 @@
 
 Bar: infidelity, gradient and final state within 1e-10 relative, equal GMRES
 iteration counts, with gmres_abstol <= 1e-13 for the parity runs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -254,12 +256,12 @@ def test_linearity_of_adjoint_operator_property(q):
 
 def test_dense_256_levels_short(q, O):
     """C4 shape (4 qudits x 4 levels: N = 256, dense random operators, order 10) at reduced column count / horizon:
-    the 8-rows-per-lane generic kernels vs the oracle."""
+    tensor-core forward sweep + 8-rows-per-lane generic adjoint sweep vs the oracle."""
     prob, controls, pcof, target, order = q.configs.dense_random(N=256, nic=2, Nc=2, nsteps=3, order=10, gmres_tol=1e-14,
                                                                  dt_norm=0.3, n_basis=12, degree=8)
     h = q.Handle(prob, controls)
     out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
-    assert h.stats()["fast_path_launches"] == 0
+    assert h.stats()["fast_path_launches"] == 1  # forward sweep on the tensor-core contraction, adjoint sweep generic
     ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
     assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
     assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
@@ -493,3 +495,49 @@ def test_dense_tensor_core_derivatives_vs_oracle(q, O, N, order, ncols):
             for j in range(m + 1):
                 assert rel(out[:, j, c], ref[:, j]) < 1e-12, (adjoint, c, j)
     h.close()
+
+
+
+@pytest.mark.parametrize("N,nic,order,nsteps,precond", [(32, 11, 10, 6, "identity"), (64, 8, 8, 5, "diagonal"),
+                                                        (64, 3, 4, 7, "identity"), (256, 9, 10, 3, "identity")])
+def test_dense_forward_sweep_tensor_core_vs_oracle(q, O, N, nic, order, nsteps, precond):
+    """eval_forward! (src/forward_evolution.jl:88-245) for dense operators with every operator application -- explicit
+    Taylor columns and GMRES matvecs -- as the CTA-wide FP64 tensor-core contraction (k_forward_dense): history, final
+    state and GMRES iteration counts vs the oracle; ragged column groups (nic not a multiple of 8); two control vectors
+    in one launch; identical iteration counts to the generic kernels."""
+    ptype = {"identity": q.IdentityPreconditioner, "diagonal": q.DiagonalHamiltonianPreconditioner}[precond]
+    prob, controls, pcof, target, _ = q.configs.dense_random(N=N, nic=nic, Nc=3, nsteps=nsteps, order=order, gmres_tol=1e-13,
+                                                             dt_norm=0.5, preconditioner_type=ptype)
+    h = q.Handle(prob, controls)
+    pcs = np.stack([pcof, 0.5 * pcof[::-1]], axis=1)
+    out = h.eval_forward(pcs, order=order)
+    assert h.stats()["fast_path_launches"] == 1, "the dense problem did not take the tensor-core sweep"
+    for b in range(2):
+        ref_h, ref_it = O.eval_forward(prob, controls, pcs[:, b], order=order)
+        assert np.abs(out["iters"][:, :, b] - ref_it).max() <= 1, "GMRES iteration counts differ by more than one"
+        assert np.mean(out["iters"][:, :, b] != ref_it) <= 0.05
+        assert rel(out["final_state"][:, :, b], ref_h[:, 0, -1, :]) < RTOL
+        for j in range(order // 2 + 1):
+            assert rel(out["history"][:, j, :, :, b], ref_h[:, j]) < RTOL
+    os.environ["QGD_DISABLE_DENSE_SWEEP"] = "1"
+    try:
+        gen = h.eval_forward(pcs, order=order)
+        assert h.stats()["fast_path_launches"] == 0
+    finally:
+        del os.environ["QGD_DISABLE_DENSE_SWEEP"]
+    assert np.abs(out["iters"] - gen["iters"]).max() <= 1
+    assert rel(out["history"], gen["history"]) < 1e-11
+    h.close()
+
+
+def test_dense_forward_sweep_save_every(q, O):
+    """saveEveryNsteps on the tensor-core sweep: stored slots equal the corresponding slots of the full history."""
+    prob, controls, pcof, target, order = q.configs.dense_random(N=32, nic=5, Nc=2, nsteps=8, order=6, gmres_tol=1e-13, dt_norm=0.5)
+    h = q.Handle(prob, controls)
+    full = h.eval_forward(pcof, order=order)
+    some = h.eval_forward(pcof, order=order, save_every=4)
+    assert h.stats()["fast_path_launches"] == 1
+    assert np.array_equal(some["history"][:, :, :, :, 0], full["history"][:, :, ::4, :, 0])
+    assert np.array_equal(some["final_state"], full["final_state"])
+    h.close()
+
