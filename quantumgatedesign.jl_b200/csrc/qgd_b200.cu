@@ -602,7 +602,7 @@ void run_adjoint(qgd_handle* h, int B, int order, const double* d_target, bool w
   h->d_gradcol.reserve((size_t)std::max(h->P, 1) * h->ncol * B * 8);
   a.gradcol = h->d_gradcol.as<double>();
   CUDA_CHECK(cudaEventRecord(h->ev[2], h->stream));
-  if (!try_backward_fast(h, d, a)) { QGD_DISPATCH_EL(el, launch_backward, h, d, a); }
+  if (!(try_backward_fast(h, d, a) || try_backward_dense(h, d, a))) { QGD_DISPATCH_EL(el, launch_backward, h, d, a); }
   CUDA_CHECK(cudaEventRecord(h->ev[3], h->stream));
   const size_t tot = std::max<size_t>((size_t)h->P * B, (size_t)B);
   k_finalize<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->P, h->ncol, B, h->d_gradcol.as<double>(),

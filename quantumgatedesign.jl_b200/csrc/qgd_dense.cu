@@ -204,10 +204,10 @@ __device__ __forceinline__ double dense_dot(const double* a, const double* b, in
 }
 
 // DiagonalHamiltonianPreconditioner (src/preconditioners.jl:108-126) on a vector in shared memory
-__device__ __forceinline__ void dense_precond(const QgdDevProb& d, double* w, int lane) {
+__device__ __forceinline__ void dense_precond(const QgdDevProb& d, double* w, int lane, int dir) {
   if (d.precond != QGD_PRECOND_DIAGONAL) return;
   const int N = d.N;
-  const double* pd = reinterpret_cast<const double*>(d.blob + d.lay.off_pre[0]);
+  const double* pd = reinterpret_cast<const double*>(d.blob + d.lay.off_pre[dir]);
   const double* dg = pd; const double* up = pd + d.N2; const double* ratio = up + N; const double* den = ratio + N;
   for (int r = lane; r < N; r += 32) {
     double xv = w[N + r] - w[r] * ratio[r];
@@ -219,20 +219,116 @@ __device__ __forceinline__ void dense_precond(const QgdDevProb& d, double* w, in
   __syncwarp();
 }
 
+// GMRES bookkeeping of the 8 columns of a CTA (shared memory; lane 0 of the owning warp writes)
+struct DenseColState {
+  int state[8], k[8], it[8];
+  double beta[8], cur[8], resb[8], acc[8];
+};
+
+// Hand the next operand v of column `col` to the contraction: forward sweep -- the W_0 tile; adjoint sweep -- the
+// tiles what_j = c_j (-dt)^j v of the reverse recursion (LHSHolderAdjoint, src/forward_evolution.jl:624-633).
+template <int M, bool ADJ>
+__device__ __forceinline__ void dense_publish(const QgdDevProb& d, double* Wt, int S, int col, int r, double v) {
+  if (!ADJ) {
+    Wt[(size_t)col * S + r] = v;
+  } else {
+#pragma unroll
+    for (int j = 0; j <= M; ++j) Wt[((size_t)j * 8 + col) * S + r] = d.a_lhs[j] * v;
+  }
+}
+
+// One GMRES event of one column after a CTA-wide operator application whose result is in `ws` (shared memory): the
+// residual of the initial guess / of a restart, or one Arnoldi step with modified Gram-Schmidt, the null-vector
+// residual recurrence and, at convergence or restart, the Givens least-squares solve and the solution update
+// (gmres_warp, qgd_warp.cuh).  One warp; every vector element r is owned by lane r % 32 throughout.
+template <int M, bool ADJ>
+__device__ __forceinline__ void dense_column_step(const QgdDevProb& d, const SweepArgs& a, const DenseSweepArgs& ds, DenseColState& cs,
+                                                  double* Wt, int S, int col, double* ws, int lane) {
+  const int N2 = d.N2, restart = N2, maxiter = N2;
+  const double tol = d.abstol;
+  const int st = cs.state[col];
+  const size_t ws_slot = (size_t)blockIdx.x * 8 + col;
+  double* X = ds.xs + ws_slot * N2;
+  const double* Bv = ds.bs + ws_slot * N2;
+  double* Vg = a.Vws + ws_slot * a.v_stride;
+  double* hcol = ds.aux + ws_slot * 3 * (N2 + 2);
+  double* nullv = hcol + (N2 + 2);
+  WarpCtx c;
+  c.d = &d; c.lane = lane; c.Hg = a.Hws + ws_slot * a.h_stride; c.yv = nullv + (N2 + 2);
+  int k = cs.k[col], it = cs.it[col], nst = DCOL_ARNOLDI;
+  double beta = cs.beta[col], cur = cs.cur[col], resb = cs.resb[col], acc = cs.acc[col];
+  if (st != DCOL_ARNOLDI) {  // v_1 = Pl^-1 (b - A x) / beta
+    for (int r = lane; r < N2; r += 32) ws[r] = Bv[r] - ws[r];
+    __syncwarp();
+    dense_precond(d, ws, lane, ADJ ? 1 : 0);
+    beta = sqrt(dense_dot(ws, ws, N2, lane));
+    const double inv = 1.0 / beta;
+    for (int r = lane; r < N2; r += 32) { const double v = ws[r] * inv; Vg[r] = v; dense_publish<M, ADJ>(d, Wt, S, col, r, v); }
+    if (st == DCOL_RESID0) cur = beta;  // a restart keeps residual.current, as the package does
+    resb = beta; acc = 1.0; k = 1;
+    if (lane == 0) nullv[0] = 1.0;
+    if (st == DCOL_RESID0 && !(cur > tol)) nst = DCOL_DONE;
+  } else {  // expand!, orthogonalize_and_normalize!, update_residual!
+    dense_precond(d, ws, lane, ADJ ? 1 : 0);
+    double dsum = 0.0;
+    for (int i = 0; i < k; ++i) {
+      const double* vi = Vg + (size_t)i * N2;
+      const double hh = dense_dot(vi, ws, N2, lane);
+      if (lane == 0) hcol[i] = hh;
+      for (int r = lane; r < N2; r += 32) ws[r] = fma(-hh, vi[r], ws[r]);
+      dsum += nullv[i] * hh;
+    }
+    const double nrm = sqrt(dense_dot(ws, ws, N2, lane));
+    const double inv = 1.0 / nrm;
+    for (int r = lane; r < N2; r += 32) { const double v = ws[r] * inv; Vg[(size_t)k * N2 + r] = v; dense_publish<M, ADJ>(d, Wt, S, col, r, v); }
+    const double nv = -(dsum / nrm);
+    if (lane == 0) { hcol[k] = nrm; nullv[k] = nv; }
+    acc += nv * nv;
+    cur = resb / sqrt(acc);
+    __syncwarp();
+    {
+      double* Hc = c.Hg + hoff(k - 1);
+      for (int i = lane; i <= k; i += 32) Hc[i] = hcol[i];
+    }
+    k += 1; it += 1;
+    if (k == restart + 1 || !(cur > tol)) {
+      const int width = k - 1;
+      __syncwarp();
+      solve_least_squares(c, width, beta);
+      for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 1:k-1] y
+        const double yj = c.yv[j];
+        const double* vj = Vg + (size_t)j * N2;
+        for (int r = lane; r < N2; r += 32) X[r] = fma(yj, vj[r], X[r]);
+      }
+      k = 1;
+      if (cur > tol && it < maxiter) {
+        nst = DCOL_RESID;
+        for (int r = lane; r < N2; r += 32) dense_publish<M, ADJ>(d, Wt, S, col, r, X[r]);
+      } else {
+        nst = DCOL_DONE;
+      }
+    } else if (it >= maxiter) {
+      nst = DCOL_DONE;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cs.state[col] = nst; cs.k[col] = k; cs.it[col] = it;
+    cs.beta[col] = beta; cs.cur[col] = cur; cs.resb[col] = resb; cs.acc[col] = acc;
+  }
+}
+
 template <int M>
 __global__ void __launch_bounds__(256, 1) k_forward_dense(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
                                                            const __grid_constant__ DenseSweepArgs ds) {
   extern __shared__ __align__(16) double Wt[];  // [(M+1)][8][S]
-  __shared__ int s_state[8], s_k[8], s_it[8];
-  __shared__ double s_beta[8], s_cur[8], s_resb[8], s_acc[8];
+  __shared__ DenseColState cs;
   const int N = d.N, N2 = d.N2, S = N2 + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int groups = (d.ncol + 7) / 8;
   const int items = a.B * groups;
   const size_t nn = (size_t)N * N, lvl = (size_t)M * 2 * nn;
   const size_t slot_sz = (size_t)N2 * (M + 1);
-  const int restart = N2, maxiter = N2;
-  const double tol = d.abstol;
 #pragma unroll 1
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / groups, c0 = (item % groups) * 8;
@@ -281,27 +377,18 @@ __global__ void __launch_bounds__(256, 1) k_forward_dense(const __grid_constant_
             a.final_state[(size_t)r + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b)] = w0;
           }
         }
-        if (lane == 0) { s_state[col] = valid ? DCOL_RESID0 : DCOL_DONE; s_it[col] = 0; s_k[col] = 1; }
+        if (lane == 0) { cs.state[col] = valid ? DCOL_RESID0 : DCOL_DONE; cs.it[col] = 0; cs.k[col] = 1; }
       }
-      if (n == d.nsteps) { __syncthreads(); break; }
       __syncthreads();
+      if (n == d.nsteps) break;
       // ---- implicit side: LHS(t_{n+1}) x = rhs by GMRES, the 8 columns in lockstep
       const double* comb1 = comb_b + (size_t)(n + 1) * lvl;
 #pragma unroll 1
       while (true) {
         dense_recursion<M>(comb1, N, Wt, S);
         for (int col = warp; col < 8; col += nwarps) {
-          const int st = s_state[col];
-          if (st == DCOL_DONE) continue;
-          const size_t ws_slot = (size_t)blockIdx.x * 8 + col;
-          double* X = ds.xs + ws_slot * N2;
-          const double* Bv = ds.bs + ws_slot * N2;
-          double* Vg = a.Vws + ws_slot * a.v_stride;
-          double* hcol = ds.aux + ws_slot * 3 * (N2 + 2);
-          double* nullv = hcol + (N2 + 2);
-          WarpCtx c;
-          c.d = &d; c.lane = lane; c.Hg = a.Hws + ws_slot * a.h_stride; c.yv = nullv + (N2 + 2);
-          double* xin = Wt + (size_t)col * S;        // operand of the next contraction
+          if (cs.state[col] == DCOL_DONE) continue;
+          const double* xin = Wt + (size_t)col * S;
           double* ws = Wt + (size_t)(8 + col) * S;   // work vector w (the W_1 tile of this column)
           for (int r = lane; r < N2; r += 32) {      // out = sum_j c_j (-dt)^j W_j  (build_LHS!, src/hermite.jl:435-457)
             double o = xin[r] * d.a_lhs[0];
@@ -310,79 +397,276 @@ __global__ void __launch_bounds__(256, 1) k_forward_dense(const __grid_constant_
             ws[r] = o;
           }
           __syncwarp();
-          int k = s_k[col], it = s_it[col], nst = DCOL_ARNOLDI;
-          double beta = s_beta[col], cur = s_cur[col], resb = s_resb[col], acc = s_acc[col];
-          if (st != DCOL_ARNOLDI) {  // residual of the initial guess / of a restart: v_1 = Pl^-1 (b - A x) / beta
-            for (int r = lane; r < N2; r += 32) ws[r] = Bv[r] - ws[r];
-            __syncwarp();
-            dense_precond(d, ws, lane);
-            beta = sqrt(dense_dot(ws, ws, N2, lane));
-            const double inv = 1.0 / beta;
-            for (int r = lane; r < N2; r += 32) { const double v = ws[r] * inv; Vg[r] = v; xin[r] = v; }
-            if (st == DCOL_RESID0) cur = beta;  // a restart keeps residual.current, as the package does
-            resb = beta; acc = 1.0; k = 1;
-            if (lane == 0) nullv[0] = 1.0;
-            if (st == DCOL_RESID0 && !(cur > tol)) nst = DCOL_DONE;
-          } else {  // one Arnoldi step: expand!, orthogonalize_and_normalize!, update_residual!
-            dense_precond(d, ws, lane);
-            double dsum = 0.0;
-            for (int i = 0; i < k; ++i) {
-              const double* vi = Vg + (size_t)i * N2;
-              const double hh = dense_dot(vi, ws, N2, lane);
-              if (lane == 0) hcol[i] = hh;
-              for (int r = lane; r < N2; r += 32) ws[r] = fma(-hh, vi[r], ws[r]);
-              dsum += nullv[i] * hh;
-            }
-            const double nrm = sqrt(dense_dot(ws, ws, N2, lane));
-            const double inv = 1.0 / nrm;
-            for (int r = lane; r < N2; r += 32) { const double v = ws[r] * inv; Vg[(size_t)k * N2 + r] = v; xin[r] = v; }
-            const double nv = -(dsum / nrm);
-            if (lane == 0) { hcol[k] = nrm; nullv[k] = nv; }
-            acc += nv * nv;
-            cur = resb / sqrt(acc);
-            __syncwarp();
-            {
-              double* Hc = c.Hg + hoff(k - 1);
-              for (int i = lane; i <= k; i += 32) Hc[i] = hcol[i];
-            }
-            k += 1; it += 1;
-            if (k == restart + 1 || !(cur > tol)) {
-              const int width = k - 1;
-              __syncwarp();
-              solve_least_squares(c, width, beta);
-              for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 1:k-1] y
-                const double yj = c.yv[j];
-                const double* vj = Vg + (size_t)j * N2;
-                for (int r = lane; r < N2; r += 32) X[r] = fma(yj, vj[r], X[r]);
-              }
-              k = 1;
-              if (cur > tol && it < maxiter) {
-                nst = DCOL_RESID;
-                for (int r = lane; r < N2; r += 32) xin[r] = X[r];
-              } else {
-                nst = DCOL_DONE;
-              }
-            } else if (it >= maxiter) {
-              nst = DCOL_DONE;
-            }
-          }
-          __syncwarp();
-          if (lane == 0) {
-            s_state[col] = nst; s_k[col] = k; s_it[col] = it;
-            s_beta[col] = beta; s_cur[col] = cur; s_resb[col] = resb; s_acc[col] = acc;
-          }
+          dense_column_step<M, false>(d, a, ds, cs, Wt, S, col, ws, lane);
         }
         __syncthreads();
         int any = 0;
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) any |= s_state[cc];
+        for (int cc = 0; cc < 8; ++cc) any |= cs.state[cc];
         if (!any) break;
       }
       if (a.iters)
         for (int col = warp; col < 8; col += nwarps)
           if (lane == 0 && c0 + col < d.ncol)
-            a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)(c0 + col) + (size_t)d.ncol * b)] = s_it[col];
-      // the barrier after the next explicit-side fill orders these reads before the next writes of s_it
+            a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)(c0 + col) + (size_t)d.ncol * b)] = cs.it[col];
+      // the barrier after the next explicit-side fill orders these reads before the next writes of cs.it
+    }
+  }
+}
+
+// ---- the dense adjoint sweep ----------------------------------------------------------------------------------
+// Raw products of one control operator with the tile Y: zKu = K Y_u, zKv = K Y_v, zSu = S Y_u, zSv = S Y_v for the 32
+// level rows of this warp (compute_inner_prod_S!/K!, src/eval_grad_discrete_adjoint.jl:764-800, as contractions).
+__device__ __forceinline__ void dense_raw4(const double* __restrict__ Kk, const double* __restrict__ Sk, int N, int r0, int lane,
+                                           const double* B, int S, double (&zKu)[4][2], double (&zKv)[4][2], double (&zSu)[4][2],
+                                           double (&zSv)[4][2]) {
+  const int ar = lane >> 2, ak = lane & 3;
+  const double* Kp = Kk + (size_t)(r0 + ar) * N + ak;
+  const double* Sp = Sk + (size_t)(r0 + ar) * N + ak;
+  const double* Bu = B + (size_t)ar * S + ak;
+  const double* Bv = Bu + N;
+#pragma unroll 2
+  for (int k0 = 0; k0 < N; k0 += 4) {
+    const double bu = Bu[k0], bv = Bv[k0];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const double aS = __ldg(Sp + (size_t)8 * t * N + k0), aK = __ldg(Kp + (size_t)8 * t * N + k0);
+      dmma884_acc(zSu[t][0], zSu[t][1], aS, bu);
+      dmma884_acc(zKv[t][0], zKv[t][1], aK, bv);
+      dmma884_acc(zSv[t][0], zSv[t][1], aS, bv);
+      dmma884_acc(zKu[t][0], zKu[t][1], aK, bu);
+    }
+  }
+}
+
+// Reverse sweep (sum_j alpha_j W_j(t))^T x on the 8 columns of a CTA: the tiles what_j = alpha_j x are filled and
+// visible; for j = M-1..0: what_{j-d} -= (1/(j+1)) A_d what_{j+1}, d = 0..j (A_d^T = -A_d); the result is the what_0
+// tile; ends with a CTA barrier.  GRAD: also the gradient inner products of this time level (recursive_magic!,
+// src/eval_grad_discrete_adjoint.jl:656-726, as in adj_sweep of qgd_warp.cuh),
+//   gK[j-i][k] += <[0 K_k; -K_k 0] w_i, what_{j+1}> / (j+1),  gS[j-i][k] += <[S_k 0; 0 S_k] w_i, what_{j+1}> / (j+1),
+// per column, with w_i the forward Taylor columns of the level (history); every warp adds the part of its level rows to
+// its own slot gp[2][M][Nc][8] (fixed summation order; the owner warp of a column adds the slots up).
+template <int M, bool GRAD>
+__device__ __forceinline__ void dense_reverse(const double* __restrict__ comb, int N, double* Wt, int S, const double* __restrict__ ops,
+                                              int Nc, const double* hist0, size_t hist_col_stride, int ncols_valid, double* gp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = 32 * warp, ar = lane >> 2, ak = lane & 3, N2 = 2 * N;
+  const size_t nn = (size_t)N * N;
+#pragma unroll 1
+  for (int j = M - 1; j >= 0; --j) {
+    const double inv = 1.0 / (double)(j + 1);
+    const double* Y = Wt + (size_t)(j + 1) * 8 * S;
+#pragma unroll 1
+    for (int dd = 0; dd <= j; ++dd) {
+      double aU[4][2], aV[4][2];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { aU[t][0] = aU[t][1] = aV[t][0] = aV[t][1] = 0.0; }
+      dense_pair(comb, dd, N, r0, lane, Y, S, aU, aV);
+      double* Wn = Wt + (size_t)(j - dd) * 8 * S;  // own rows only: no other warp touches them in this stage
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int row = r0 + 8 * t + ar;
+        Wn[(size_t)(2 * ak) * S + row] -= aU[t][0] * inv;
+        Wn[(size_t)(2 * ak + 1) * S + row] -= aU[t][1] * inv;
+        Wn[(size_t)(2 * ak) * S + N + row] -= aV[t][0] * inv;
+        Wn[(size_t)(2 * ak + 1) * S + N + row] -= aV[t][1] * inv;
+      }
+    }
+    if (GRAD) {
+#pragma unroll 1
+      for (int k = 0; k < Nc; ++k) {
+        double zKu[4][2], zKv[4][2], zSu[4][2], zSv[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          zKu[t][0] = zKu[t][1] = zKv[t][0] = zKv[t][1] = 0.0;
+          zSu[t][0] = zSu[t][1] = zSv[t][0] = zSv[t][1] = 0.0;
+        }
+        dense_raw4(ops + ((size_t)(k + 1) * 2 + 0) * nn, ops + ((size_t)(k + 1) * 2 + 1) * nn, N, r0, lane, Y, S, zKu, zKv, zSu, zSv);
+#pragma unroll 1
+        for (int i = 0; i <= j; ++i) {
+          double pK[2] = {0.0, 0.0}, pS[2] = {0.0, 0.0};
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int col = 2 * ak + cc;
+            if (col < ncols_valid) {
+              const double* wi = hist0 + hist_col_stride * col + (size_t)i * N2;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int row = r0 + 8 * t + ar;
+                const double wu = __ldg(wi + row), wv = __ldg(wi + N + row);
+                pK[cc] += wv * zKu[t][cc] - wu * zKv[t][cc];
+                pS[cc] += wu * zSu[t][cc] + wv * zSv[t][cc];
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              pK[cc] += __shfl_xor_sync(FULL_MASK, pK[cc], o);
+              pS[cc] += __shfl_xor_sync(FULL_MASK, pS[cc], o);
+            }
+          }
+          if (ar == 0) {
+            const int rr = j - i;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              gp[(((size_t)0 * M + rr) * Nc + k) * 8 + 2 * ak + cc] += inv * pK[cc];
+              gp[(((size_t)1 * M + rr) * Nc + k) * 8 + 2 * ak + cc] -= inv * pS[cc];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// eval_adjoint! + accumulate_gradient! (src/forward_evolution.jl:352-483, src/eval_grad_discrete_adjoint.jl:582-726)
+// for dense Hamiltonians; the structure of k_backward (qgd_kernels.cuh) with 8 columns per CTA in lockstep.
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_backward_dense(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
+                                                            const __grid_constant__ DenseSweepArgs ds, const double* __restrict__ ops,
+                                                            const QgdDevControl* __restrict__ ctrls) {
+  extern __shared__ __align__(16) double Wt[];  // [(M+1)][8][S] | gpart [nwarps][2][M][Nc][8] | gred [2][M][Nc][8]
+  __shared__ DenseColState cs;
+  const int N = d.N, N2 = d.N2, S = N2 + 4, Nc = d.Nc, P = d.P, Nt = d.nsteps + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int G = 2 * M * Nc * 8;
+  double* gpart = Wt + (size_t)(M + 1) * 8 * S;
+  double* gred = gpart + (size_t)nwarps * G;
+  double* gp = gpart + (size_t)warp * G;
+  const int groups = (d.ncol + 7) / 8;
+  const int items = a.B * groups;
+  const size_t nn = (size_t)N * N, lvl = (size_t)M * 2 * nn;
+  const size_t slot_sz = (size_t)N2 * (M + 1), tab_stride = (size_t)2 * (M + 1) * P;
+  const size_t hist_col_stride = slot_sz * Nt;
+
+  // what_j = alpha_j lambda for the owned columns; zero the gradient slot of this warp
+  auto fill_tiles = [&](const double* alpha, double sign) {
+    for (int col = warp; col < 8; col += nwarps) {
+      const double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+      for (int r = lane; r < N2; r += 32) {
+        const double x = X[r];
+#pragma unroll
+        for (int j = 0; j <= M; ++j) Wt[((size_t)j * 8 + col) * S + r] = sign * alpha[j] * x;
+      }
+    }
+    for (int i = lane; i < G; i += 32) gp[i] = 0.0;
+  };
+  // owner warps: add the per-warp slots up (fixed order)
+  auto reduce_g = [&]() {
+    for (int col = warp; col < 8; col += nwarps)
+      for (int i = lane; i < 2 * M * Nc; i += 32) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += gpart[(size_t)w * G + (size_t)i * 8 + col];
+        gred[(size_t)i * 8 + col] = s;
+      }
+  };
+  // grad[theta] -= sum_r d/dtheta p^(r)/r! gK[r][k(theta)] + d/dtheta q^(r)/r! gS[r][k(theta)]   (accumulate_grad)
+  auto accumulate = [&](int b, int c0, const double* table_n) {
+    for (int col = warp; col < 8; col += nwarps) {
+      const int cl = c0 + col;
+      if (cl >= d.ncol) continue;
+      double* gacc = a.gradcol + (size_t)P * ((size_t)cl + (size_t)d.ncol * b);
+      for (int k = 0; k < Nc; ++k) {
+        const int off = ctrls[k].offset, nco = ctrls[k].ncoeff;
+        for (int t = lane; t < nco; t += 32) {
+          double s = 0.0;
+          for (int r = 0; r < M; ++r) {
+            s = fma(table_n[((size_t)0 * (M + 1) + r) * P + off + t], gred[(((size_t)0 * M + r) * Nc + k) * 8 + col], s);
+            s = fma(table_n[((size_t)1 * (M + 1) + r) * P + off + t], gred[(((size_t)1 * M + r) * Nc + k) * 8 + col], s);
+          }
+          gacc[off + t] -= s;
+        }
+      }
+    }
+  };
+
+#pragma unroll 1
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / groups, c0 = (item % groups) * 8;
+    const double* comb_b = ds.comb + (size_t)b * Nt * lvl;
+    const double* hist_b = a.history + hist_col_stride * ((size_t)c0 + (size_t)d.ncol * b);  // column c0, level 0
+    const int ncv = d.ncol - c0;
+    for (int col = warp; col < 8; col += nwarps) {
+      const int cl = c0 + col;
+      const bool valid = cl < d.ncol;
+      double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+      const double* term = a.terminal + (size_t)N2 * ((size_t)(d.col0 + cl) + (size_t)d.nic * b);
+      double* lam0 = (valid && a.lambda0) ? a.lambda0 + (size_t)N2 * Nt * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
+      for (int r = lane; r < N2; r += 32) {
+        const double x = valid ? term[r] : 0.0;
+        X[r] = x;
+        if (lam0) lam0[(size_t)N2 * d.nsteps + r] = x;
+      }
+      if (valid) {
+        double* gacc = a.gradcol + (size_t)P * ((size_t)cl + (size_t)d.ncol * b);
+        for (int t = lane; t < P; t += 32) gacc[t] = 0.0;
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int n = d.nsteps - 1; n >= 0; --n) {
+      // ---- implicit side: time level n+1, alpha_j = -c_j (-dt)^j
+      fill_tiles(d.a_lhs, -1.0);
+      __syncthreads();
+      dense_reverse<M, true>(comb_b + (size_t)(n + 1) * lvl, N, Wt, S, ops, Nc, hist_b + slot_sz * (n + 1), hist_col_stride, ncv, gp);
+      reduce_g();
+      __syncthreads();
+      accumulate(b, c0, d.table + (size_t)(n + 1) * tab_stride);
+      // ---- explicit side: time level n, alpha_j = c_j dt^j; what_0 = R(t_n)^T lambda_{n+1}
+      fill_tiles(d.a_rhs, 1.0);
+      __syncthreads();
+      dense_reverse<M, true>(comb_b + (size_t)n * lvl, N, Wt, S, ops, Nc, hist_b + slot_sz * n, hist_col_stride, ncv, gp);
+      reduce_g();
+      __syncthreads();
+      accumulate(b, c0, d.table + (size_t)n * tab_stride);
+      if (n == 0) { __syncthreads(); break; }
+      // ---- lambda_n: LHS(t_n)^T lambda_n = R(t_n)^T lambda_{n+1} + f_n, x0 = lambda_{n+1} (forward_evolution.jl:450)
+      for (int col = warp; col < 8; col += nwarps) {
+        const int cl = c0 + col;
+        const bool valid = cl < d.ncol;
+        double* Bv = ds.bs + ((size_t)blockIdx.x * 8 + col) * N2;
+        const double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+        const double* wn = hist_b + hist_col_stride * col + slot_sz * n;  // w_n (Taylor column 0)
+        const int* wcol = reinterpret_cast<const int*>(d.blob + d.lay.off_wcol);
+        const double* wval = reinterpret_cast<const double*>(d.blob + d.lay.off_wval);
+        const double fsc = -2.0 * d.dt / d.tf;  // guard forcing f_n = -(2 dt/tf) W w_n (interior point: weight 1)
+        for (int r = lane; r < N2; r += 32) {
+          double g = 0.0;
+          if (valid)
+            for (int s = 0; s < d.lay.LW; ++s) g = fma(wval[(size_t)s * N2 + r], __ldg(wn + wcol[(size_t)s * N2 + r]), g);
+          Bv[r] = fma(fsc, g, Wt[(size_t)col * S + r]);
+        }
+        for (int r = lane; r < N2; r += 32) dense_publish<M, true>(d, Wt, S, col, r, X[r]);
+        if (lane == 0) { cs.state[col] = valid ? DCOL_RESID0 : DCOL_DONE; cs.it[col] = 0; cs.k[col] = 1; }
+      }
+      __syncthreads();
+      const double* combn = comb_b + (size_t)n * lvl;
+#pragma unroll 1
+      while (true) {
+        dense_reverse<M, false>(combn, N, Wt, S, nullptr, 0, nullptr, 0, 0, nullptr);
+        for (int col = warp; col < 8; col += nwarps) {
+          if (cs.state[col] == DCOL_DONE) continue;
+          dense_column_step<M, true>(d, a, ds, cs, Wt, S, col, Wt + (size_t)col * S, lane);
+        }
+        __syncthreads();
+        int any = 0;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) any |= cs.state[cc];
+        if (!any) break;
+      }
+      for (int col = warp; col < 8; col += nwarps) {
+        const int cl = c0 + col;
+        if (cl >= d.ncol) continue;
+        const double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+        if (a.lambda0) {
+          double* lam0 = a.lambda0 + (size_t)N2 * ((size_t)n + (size_t)Nt * ((size_t)cl + (size_t)d.ncol * b));
+          for (int r = lane; r < N2; r += 32) lam0[r] = X[r];
+        }
+        if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = cs.it[col];
+      }
     }
   }
 }
@@ -447,24 +731,29 @@ void launch_forward_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs a
   CUDA_CHECK(cudaGetLastError());
   h->stats.kernel_launches++;
 }
-}  // namespace
+template <int M>
+void launch_backward_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs a, qgd::DenseSweepArgs ds, int grid, size_t smem) {
+  CUDA_CHECK(cudaFuncSetAttribute(qgd::k_backward_dense<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  qgd::k_backward_dense<M><<<grid, d.N, smem, h->stream>>>(d, a, ds, h->d_dense.as<double>(), h->d_ctrls.as<QgdDevControl>());
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+}
 
-// Forward sweep of a dense problem on the tensor-core contraction (k_forward_dense).  false: not applicable (sparse or
-// register-operator problem, LU preconditioner, level count not a multiple of 32, the per-level operators of the whole
-// time grid do not fit the device memory) -- the caller then uses the generic kernels.
-bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a_in) {
+// Shared set-up of the two dense sweeps: applicability, the per-level combined operators of the whole time grid,
+// Krylov / state workspaces for `grid` CTAs of 8 columns.  extra_smem: bytes beyond the Taylor tiles.
+bool prepare_dense_sweep(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs& a, qgd::DenseSweepArgs& ds, int& grid, size_t& smem,
+                         size_t extra_smem) {
   const int m = d.m, N = h->N, N2 = h->N2;
   if (getenv("QGD_DISABLE_DENSE_SWEEP")) return false;
   if (!dense_derivs_applicable(h, m) || h->precond == QGD_PRECOND_LU || h->Nc < 1) return false;
-  const size_t smem = (size_t)(m + 1) * 8 * (N2 + 4) * 8;
+  smem = (size_t)(m + 1) * 8 * (N2 + 4) * 8 + extra_smem;
   if (smem + 512 > h->prop.sharedMemPerBlockOptin) return false;
-  if ((size_t)a_in.B * (h->nsteps + 1) > 65535) return false;  // grid.y of the operator combination
-  const size_t nn = (size_t)N * N, levels = (size_t)a_in.B * (h->nsteps + 1);
+  if ((size_t)a.B * (h->nsteps + 1) > 65535) return false;  // grid.y of the operator combination
+  const size_t nn = (size_t)N * N, levels = (size_t)a.B * (h->nsteps + 1);
   const size_t comb_bytes = levels * m * 2 * nn * 8;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   if (comb_bytes > h->d_comb.cap && comb_bytes > (free_b / 10) * 7) return false;
-  qgd::SweepArgs a = a_in;
   if (h->d_dense.cap == 0) {
     h->d_dense.reserve(h->dense_ops.size() * 8);
     CUDA_CHECK(cudaMemcpyAsync(h->d_dense.p, h->dense_ops.data(), h->dense_ops.size() * 8, cudaMemcpyHostToDevice, h->stream));
@@ -472,13 +761,13 @@ bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs&
   h->d_comb.reserve(comb_bytes);
   {
     const size_t total = (size_t)m * 2 * nn;
-    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 1024), (unsigned)levels);
-    qgd::k_dense_combine_levels<<<grid, 256, 0, h->stream>>>(h->d_dense.as<double>(), N, h->Nc, m, a.cvals, h->d_comb.as<double>());
+    dim3 cgrid((unsigned)std::min<size_t>((total + 255) / 256, 1024), (unsigned)levels);
+    qgd::k_dense_combine_levels<<<cgrid, 256, 0, h->stream>>>(h->d_dense.as<double>(), N, h->Nc, m, a.cvals, h->d_comb.as<double>());
     CUDA_CHECK(cudaGetLastError());
     h->stats.kernel_launches++;
   }
   const int groups = (h->ncol + 7) / 8;
-  const int grid = std::max(1, std::min(a.B * groups, h->prop.multiProcessorCount));
+  grid = std::max(1, std::min(a.B * groups, h->prop.multiProcessorCount));
   const size_t slots = (size_t)grid * 8;
   a.v_stride = (size_t)(N2 + 1) * N2;
   a.h_stride = (size_t)N2 * (N2 + 3) / 2 + 2;
@@ -487,18 +776,51 @@ bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs&
   a.Vws = h->d_V.as<double>();
   a.Hws = h->d_H.as<double>();
   h->d_dense_ws.reserve(slots * (2 * (size_t)N2 + 3 * ((size_t)N2 + 2)) * 8);
-  qgd::DenseSweepArgs ds{};
   ds.comb = h->d_comb.as<double>();
   ds.xs = h->d_dense_ws.as<double>();
   ds.bs = ds.xs + slots * N2;
   ds.aux = ds.bs + slots * N2;
-  switch (m) {
+  return true;
+}
+}  // namespace
+
+// Forward sweep of a dense problem on the tensor-core contraction (k_forward_dense).  false: not applicable (sparse or
+// register-operator problem, LU preconditioner, level count not a multiple of 32, the per-level operators of the whole
+// time grid do not fit the device memory) -- the caller then uses the generic kernels.
+bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a_in) {
+  qgd::SweepArgs a = a_in;
+  qgd::DenseSweepArgs ds{};
+  int grid = 0;
+  size_t smem = 0;
+  if (!prepare_dense_sweep(h, d, a, ds, grid, smem, 0)) return false;
+  switch (d.m) {
     case 1: launch_forward_dense_t<1>(h, d, a, ds, grid, smem); break;
     case 2: launch_forward_dense_t<2>(h, d, a, ds, grid, smem); break;
     case 3: launch_forward_dense_t<3>(h, d, a, ds, grid, smem); break;
     case 4: launch_forward_dense_t<4>(h, d, a, ds, grid, smem); break;
     case 5: launch_forward_dense_t<5>(h, d, a, ds, grid, smem); break;
     default: launch_forward_dense_t<6>(h, d, a, ds, grid, smem); break;
+  }
+  h->stats.fast_path_launches++;
+  return true;
+}
+
+// Adjoint sweep + gradient accumulation of a dense problem (k_backward_dense); needs the full history (saveEveryNsteps 1)
+// on the device.  false: not applicable (as above, or the gradient slots do not fit beside the Taylor tiles).
+bool try_backward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a_in) {
+  qgd::SweepArgs a = a_in;
+  qgd::DenseSweepArgs ds{};
+  int grid = 0;
+  size_t smem = 0;
+  const size_t G = (size_t)2 * d.m * h->Nc * 8;
+  if (!prepare_dense_sweep(h, d, a, ds, grid, smem, (size_t)(h->N / 32 + 1) * G * 8)) return false;
+  switch (d.m) {
+    case 1: launch_backward_dense_t<1>(h, d, a, ds, grid, smem); break;
+    case 2: launch_backward_dense_t<2>(h, d, a, ds, grid, smem); break;
+    case 3: launch_backward_dense_t<3>(h, d, a, ds, grid, smem); break;
+    case 4: launch_backward_dense_t<4>(h, d, a, ds, grid, smem); break;
+    case 5: launch_backward_dense_t<5>(h, d, a, ds, grid, smem); break;
+    default: launch_backward_dense_t<6>(h, d, a, ds, grid, smem); break;
   }
   h->stats.fast_path_launches++;
   return true;

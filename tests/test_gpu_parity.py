@@ -256,12 +256,12 @@ def test_linearity_of_adjoint_operator_property(q):
 
 def test_dense_256_levels_short(q, O):
     """C4 shape (4 qudits x 4 levels: N = 256, dense random operators, order 10) at reduced column count / horizon:
-    tensor-core forward sweep + 8-rows-per-lane generic adjoint sweep vs the oracle."""
+    tensor-core forward and adjoint sweeps (qgd_dense.cu) vs the oracle."""
     prob, controls, pcof, target, order = q.configs.dense_random(N=256, nic=2, Nc=2, nsteps=3, order=10, gmres_tol=1e-14,
                                                                  dt_norm=0.3, n_basis=12, degree=8)
     h = q.Handle(prob, controls)
     out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
-    assert h.stats()["fast_path_launches"] == 1  # forward sweep on the tensor-core contraction, adjoint sweep generic
+    assert h.stats()["fast_path_launches"] == 2  # forward and adjoint sweep on the tensor-core contraction
     ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
     assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
     assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
@@ -539,5 +539,43 @@ def test_dense_forward_sweep_save_every(q, O):
     assert h.stats()["fast_path_launches"] == 1
     assert np.array_equal(some["history"][:, :, :, :, 0], full["history"][:, :, ::4, :, 0])
     assert np.array_equal(some["final_state"], full["final_state"])
+    h.close()
+
+
+@pytest.mark.parametrize("N,nic,order,nsteps,precond,guard", [(32, 11, 10, 5, "identity", True), (64, 8, 8, 4, "diagonal", False),
+                                                              (64, 3, 4, 6, "identity", True), (32, 8, 2, 5, "identity", False)])
+def test_dense_adjoint_sweep_tensor_core_vs_oracle(q, O, N, nic, order, nsteps, precond, guard):
+    """discrete_adjoint! for dense operators with both sweeps on the FP64 tensor cores (k_forward_dense, k_backward_dense):
+    gradient, infidelity, guard penalty, lambda and iteration counts vs the oracle and vs the generic kernels; ragged
+    column groups, a dense random guard projector (guard forcing in the adjoint right-hand side), two control vectors."""
+    ptype = {"identity": q.IdentityPreconditioner, "diagonal": q.DiagonalHamiltonianPreconditioner}[precond]
+    prob, controls, pcof, target, _ = q.configs.dense_random(N=N, nic=nic, Nc=3, nsteps=nsteps, order=order, gmres_tol=1e-13,
+                                                             dt_norm=0.5, preconditioner_type=ptype)
+    if guard:  # diagonal 0/1 projector on the upper quarter of the levels, as guard_projector builds it
+        w = np.zeros(2 * N)
+        w[3 * N // 4:N] = 1.0
+        w[N + 3 * N // 4:] = 1.0
+        prob.guard_subspace_projector = np.diag(w)
+    tgt = q.complex_to_real(target)
+    h = q.Handle(prob, controls)
+    pcs = np.stack([pcof, 0.5 * pcof[::-1]], axis=1)
+    out = h.discrete_adjoint(pcs, tgt, order=order, want_lambda=True, want_iters=True)
+    assert h.stats()["fast_path_launches"] == 2, "the dense problem did not take the tensor-core sweeps"
+    for b in range(2):
+        ref = O.discrete_adjoint(prob, controls, pcs[:, b], target, order=order)
+        assert np.abs(out["iters_fwd"][:, :, b] - ref["iters_fwd"]).max() <= 1
+        assert np.abs(out["iters_adj"][:, :, b] - ref["iters_adj"]).max() <= 1
+        assert abs(out["infidelity"][b] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+        assert abs(out["guard_penalty"][b] - ref["guard_penalty"]) <= RTOL * max(abs(ref["guard_penalty"]), 1e-300)
+        assert rel(out["grad"][:, b], ref["grad"]) < RTOL
+        assert rel(out["lambda_history"][:, 0, :, :, b], ref["lambda_history"][:, 0]) < 1e-9
+    os.environ["QGD_DISABLE_DENSE_SWEEP"] = "1"
+    try:
+        gen = h.discrete_adjoint(pcs, tgt, order=order, want_iters=True)
+        assert h.stats()["fast_path_launches"] == 0
+    finally:
+        del os.environ["QGD_DISABLE_DENSE_SWEEP"]
+    assert rel(out["grad"], gen["grad"]) < 1e-10
+    assert np.abs(out["iters_adj"] - gen["iters_adj"]).max() <= 1
     h.close()
 

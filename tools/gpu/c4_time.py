@@ -22,7 +22,7 @@ m = order // 2
 # dense flops: one A_j apply on one column 8 N^2 (K_j, S_j pre-combined), m(m+1)/2 applies per operator evaluation
 evals = (2 * nsteps + 1) * nic + itf.sum() + (3 * nsteps - 1) * nic + ita.sum()
 flops = 8.0 * 256 ** 2 * (m * (m + 1) / 2) * evals
-res = dict(nsteps=nsteps, nic=nic, wall_s=wall, forward_ms=st["last_forward_ms"], backward_ms=st["last_backward_ms"],
+res = dict(nsteps=nsteps, nic=nic, wall_s=wall, total_ms=st["last_total_ms"], forward_ms=st["last_forward_ms"], backward_ms=st["last_backward_ms"],
            gmres_iters_per_step_fwd=float(itf.mean()), gmres_iters_per_step_adj=float(ita.mean()),
            fast_path_launches=st["fast_path_launches"], algorithmic_tflop=flops / 1e12,
            achieved_tflops=flops / 1e12 / ((st["last_forward_ms"] + st["last_backward_ms"]) * 1e-3),
