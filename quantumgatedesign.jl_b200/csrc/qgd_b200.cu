@@ -591,7 +591,7 @@ void run_adjoint(qgd_handle* h, int B, int order, const double* d_target, bool w
     CUDA_CHECK(cudaMemsetAsync(h->d_iters_a.p, 0, (size_t)h->nsteps * h->ncol * B * 4, h->stream));
     a.iters_term = h->d_iters_t.as<int>();
   }
-  QGD_DISPATCH_EL(el, launch_terminal, h, d, a);
+  if (!try_terminal_dense(h, d, a)) { QGD_DISPATCH_EL(el, launch_terminal, h, d, a); }
   a.iters = want_iters ? h->d_iters_a.as<int>() : nullptr;
   if (want_lambda0) {
     const size_t sz = (size_t)h->N2 * (h->nsteps + 1) * h->ncol * B * 8;

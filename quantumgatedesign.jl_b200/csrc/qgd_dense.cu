@@ -222,7 +222,7 @@ __device__ __forceinline__ void dense_precond(const QgdDevProb& d, double* w, in
 // GMRES bookkeeping of the 8 columns of a CTA (shared memory; lane 0 of the owning warp writes)
 struct DenseColState {
   int state[8], k[8], it[8];
-  double beta[8], cur[8], resb[8], acc[8];
+  double beta[8], cur[8], resb[8], acc[8], tol[8];
 };
 
 // Hand the next operand v of column `col` to the contraction: forward sweep -- the W_0 tile; adjoint sweep -- the
@@ -243,9 +243,9 @@ __device__ __forceinline__ void dense_publish(const QgdDevProb& d, double* Wt, i
 // (gmres_warp, qgd_warp.cuh).  One warp; every vector element r is owned by lane r % 32 throughout.
 template <int M, bool ADJ>
 __device__ __forceinline__ void dense_column_step(const QgdDevProb& d, const SweepArgs& a, const DenseSweepArgs& ds, DenseColState& cs,
-                                                  double* Wt, int S, int col, double* ws, int lane) {
-  const int N2 = d.N2, restart = N2, maxiter = N2;
-  const double tol = d.abstol;
+                                                  double* Wt, int S, int col, double* ws, int lane, int restart, double reltol, int pdir) {
+  const int N2 = d.N2, maxiter = N2;
+  double tol = cs.tol[col];
   const int st = cs.state[col];
   const size_t ws_slot = (size_t)blockIdx.x * 8 + col;
   double* X = ds.xs + ws_slot * N2;
@@ -260,16 +260,19 @@ __device__ __forceinline__ void dense_column_step(const QgdDevProb& d, const Swe
   if (st != DCOL_ARNOLDI) {  // v_1 = Pl^-1 (b - A x) / beta
     for (int r = lane; r < N2; r += 32) ws[r] = Bv[r] - ws[r];
     __syncwarp();
-    dense_precond(d, ws, lane, ADJ ? 1 : 0);
+    if (pdir >= 0) dense_precond(d, ws, lane, pdir);
     beta = sqrt(dense_dot(ws, ws, N2, lane));
     const double inv = 1.0 / beta;
     for (int r = lane; r < N2; r += 32) { const double v = ws[r] * inv; Vg[r] = v; dense_publish<M, ADJ>(d, Wt, S, col, r, v); }
-    if (st == DCOL_RESID0) cur = beta;  // a restart keeps residual.current, as the package does
+    if (st == DCOL_RESID0) {  // a restart keeps residual.current and the tolerance, as the package does
+      cur = beta;
+      tol = (reltol < 0.0) ? d.abstol : fmax(reltol * beta, d.abstol);  // reltol < 0: the time-stepping solves
+    }
     resb = beta; acc = 1.0; k = 1;
     if (lane == 0) nullv[0] = 1.0;
     if (st == DCOL_RESID0 && !(cur > tol)) nst = DCOL_DONE;
   } else {  // expand!, orthogonalize_and_normalize!, update_residual!
-    dense_precond(d, ws, lane, ADJ ? 1 : 0);
+    if (pdir >= 0) dense_precond(d, ws, lane, pdir);
     double dsum = 0.0;
     for (int i = 0; i < k; ++i) {
       const double* vi = Vg + (size_t)i * N2;
@@ -314,7 +317,7 @@ __device__ __forceinline__ void dense_column_step(const QgdDevProb& d, const Swe
   __syncwarp();
   if (lane == 0) {
     cs.state[col] = nst; cs.k[col] = k; cs.it[col] = it;
-    cs.beta[col] = beta; cs.cur[col] = cur; cs.resb[col] = resb; cs.acc[col] = acc;
+    cs.beta[col] = beta; cs.cur[col] = cur; cs.resb[col] = resb; cs.acc[col] = acc; cs.tol[col] = tol;
   }
 }
 
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(256, 1) k_forward_dense(const __grid_constant_
             ws[r] = o;
           }
           __syncwarp();
-          dense_column_step<M, false>(d, a, ds, cs, Wt, S, col, ws, lane);
+          dense_column_step<M, false>(d, a, ds, cs, Wt, S, col, ws, lane, N2, -1.0, 0);
         }
         __syncthreads();
         int any = 0;
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(256, 1) k_backward_dense(const __grid_constant
         dense_reverse<M, false>(combn, N, Wt, S, nullptr, 0, nullptr, 0, 0, nullptr);
         for (int col = warp; col < 8; col += nwarps) {
           if (cs.state[col] == DCOL_DONE) continue;
-          dense_column_step<M, true>(d, a, ds, cs, Wt, S, col, Wt + (size_t)col * S, lane);
+          dense_column_step<M, true>(d, a, ds, cs, Wt, S, col, Wt + (size_t)col * S, lane, N2, -1.0, 1);
         }
         __syncthreads();
         int any = 0;
@@ -668,6 +671,111 @@ __global__ void __launch_bounds__(256, 1) k_backward_dense(const __grid_constant
         if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = cs.it[col];
       }
     }
+  }
+}
+
+
+// Infidelity and terminal condition (infidelity_real, src/infidelity.jl:7-18; compute_terminal_condition,
+// src/eval_grad_discrete_adjoint.jl:1-67) for dense Hamiltonians: LHS(tf)^T lambda_N = (2/N_ess^2)(<psi_N,R> R +
+// <psi_N,T> T) + f_N, un-preconditioned GMRES with restart 20 and tol = max(reltol beta_0, abstol) as the reference's
+// gmres! call, the operator application being the CTA-wide tensor-core reverse recursion.
+//   sequential (default): one CTA per control vector solves the columns one after the other and, like the reference,
+//     leaves the solution of column i-1 in the buffer as the initial guess of column i (:60-64) -- same iteration counts
+//     and the same lambda_N as the reference; one of the 8 contraction columns is used.
+//   parallel (QGD_DENSE_TERMINAL_PARALLEL): 8 columns per CTA in lockstep, every column from a zero guess -- lambda_N
+//     then agrees with the reference to the GMRES tolerance only.
+template <int M>
+__global__ void __launch_bounds__(256, 1) k_terminal_dense(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
+                                                            const __grid_constant__ DenseSweepArgs ds, const int sequential) {
+  extern __shared__ __align__(16) double Wt[];  // [(M+1)][8][S]
+  __shared__ DenseColState cs;
+  __shared__ double s_red[2][8];
+  const int N = d.N, N2 = d.N2, S = N2 + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int groups = sequential ? 1 : (d.nic + 7) / 8;
+  const int items = a.B * groups;
+  const size_t nn = (size_t)N * N, lvl = (size_t)M * 2 * nn;
+  const int restart = N2 < 20 ? N2 : 20;
+  const int nsub = sequential ? d.nic : 1, nact = sequential ? 1 : 8;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / groups;
+    const double* psi = a.final_all + (size_t)N2 * d.nic * b;
+    // <psi_N, R> and <psi_N, T>, T = [R_v; -R_u], over ALL columns
+    double dR = 0.0, dT = 0.0;
+    for (int col = 0; col < d.nic; ++col) {
+      const double* p = psi + (size_t)N2 * col;
+      const double* R = a.target + (size_t)N2 * col;
+      for (int r = threadIdx.x; r < N; r += blockDim.x) {
+        const double pu = p[r], pv = p[N + r], Ru = R[r], Rv = R[N + r];
+        dR += pu * Ru + pv * Rv;
+        dT += pu * Rv - pv * Ru;
+      }
+    }
+    dR = warp_sum(dR);
+    dT = warp_sum(dT);
+    __syncthreads();  // previous item: everybody is done with s_red and cs
+    if (lane == 0) { s_red[0][warp] = dR; s_red[1][warp] = dT; }
+    __syncthreads();
+    dR = 0.0; dT = 0.0;
+    for (int w = 0; w < nwarps; ++w) { dR += s_red[0][w]; dT += s_red[1][w]; }
+    const double ness2 = (double)d.Ness * (double)d.Ness;
+    if (item % groups == 0 && threadIdx.x == 0) a.infidelity[b] = 1.0 - (dR * dR + dT * dT) / ness2;
+    const double sc = 2.0 / ness2;
+    const double fsc = -2.0 * d.dt / d.tf * 0.5;  // forcing[:, end, :]: trapezoid weight 1/2
+#pragma unroll 1
+   for (int sub = 0; sub < nsub; ++sub) {
+    const int c0 = sequential ? sub : (item % groups) * 8;
+    for (int col = warp; col < 8; col += nwarps) {
+      const int cg = c0 + col;
+      const bool valid = col < nact && cg < d.nic;
+      double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+      double* Bv = ds.bs + ((size_t)blockIdx.x * 8 + col) * N2;
+      const double* p = psi + (size_t)N2 * cg;
+      const double* R = a.target + (size_t)N2 * cg;
+      const int* wcol = reinterpret_cast<const int*>(d.blob + d.lay.off_wcol);
+      const double* wval = reinterpret_cast<const double*>(d.blob + d.lay.off_wval);
+      for (int r = lane; r < N; r += 32) {
+        double gu = 0.0, gv = 0.0, Ru = 0.0, Rv = 0.0;
+        if (valid) {
+          for (int s = 0; s < d.lay.LW; ++s) {
+            gu = fma(wval[(size_t)s * N2 + r], p[wcol[(size_t)s * N2 + r]], gu);
+            gv = fma(wval[(size_t)s * N2 + N + r], p[wcol[(size_t)s * N2 + N + r]], gv);
+          }
+          Ru = R[r]; Rv = R[N + r];
+        }
+        Bv[r] = (dR * Ru + dT * Rv) * sc + fsc * gu;
+        Bv[N + r] = (dR * Rv + dT * (-Ru)) * sc + fsc * gv;
+        if (!sequential || sub == 0) { X[r] = 0.0; X[N + r] = 0.0; }
+      }
+      for (int r = lane; r < N2; r += 32) dense_publish<M, true>(d, Wt, S, col, r, valid ? X[r] : 0.0);
+      if (lane == 0) { cs.state[col] = valid ? DCOL_RESID0 : DCOL_DONE; cs.it[col] = 0; cs.k[col] = 1; }
+    }
+    __syncthreads();
+    const double* combN = ds.comb + ((size_t)b * (d.nsteps + 1) + d.nsteps) * lvl;  // controls at t = tf
+#pragma unroll 1
+    while (true) {
+      dense_reverse<M, false>(combN, N, Wt, S, nullptr, 0, nullptr, 0, 0, nullptr);
+      for (int col = warp; col < 8; col += nwarps) {
+        if (cs.state[col] == DCOL_DONE) continue;
+        dense_column_step<M, true>(d, a, ds, cs, Wt, S, col, Wt + (size_t)col * S, lane, restart, d.reltol, -1);
+      }
+      __syncthreads();
+      int any = 0;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) any |= cs.state[cc];
+      if (!any) break;
+    }
+    for (int col = warp; col < 8; col += nwarps) {
+      const int cg = c0 + col;
+      if (col >= nact || cg >= d.nic) continue;
+      const double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+      double* out = a.terminal_out + (size_t)N2 * ((size_t)cg + (size_t)d.nic * b);
+      for (int r = lane; r < N2; r += 32) out[r] = X[r];
+      if (a.iters_term && lane == 0) a.iters_term[(size_t)cg + (size_t)d.nic * b] = cs.it[col];
+    }
+    __syncthreads();  // cs and the tiles are rewritten by the next column
+   }
   }
 }
 
@@ -732,6 +840,13 @@ void launch_forward_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs a
   h->stats.kernel_launches++;
 }
 template <int M>
+void launch_terminal_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs a, qgd::DenseSweepArgs ds, int grid, size_t smem, int seq) {
+  CUDA_CHECK(cudaFuncSetAttribute(qgd::k_terminal_dense<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  qgd::k_terminal_dense<M><<<grid, d.N, smem, h->stream>>>(d, a, ds, seq);
+  CUDA_CHECK(cudaGetLastError());
+  h->stats.kernel_launches++;
+}
+template <int M>
 void launch_backward_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs a, qgd::DenseSweepArgs ds, int grid, size_t smem) {
   CUDA_CHECK(cudaFuncSetAttribute(qgd::k_backward_dense<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   qgd::k_backward_dense<M><<<grid, d.N, smem, h->stream>>>(d, a, ds, h->d_dense.as<double>(), h->d_ctrls.as<QgdDevControl>());
@@ -742,12 +857,12 @@ void launch_backward_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs 
 // Shared set-up of the two dense sweeps: applicability, the per-level combined operators of the whole time grid,
 // Krylov / state workspaces for `grid` CTAs of 8 columns.  extra_smem: bytes beyond the Taylor tiles.
 bool prepare_dense_sweep(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs& a, qgd::DenseSweepArgs& ds, int& grid, size_t& smem,
-                         size_t extra_smem) {
+                         size_t extra_smem, int ncols) {
   const int m = d.m, N = h->N, N2 = h->N2;
   if (getenv("QGD_DISABLE_DENSE_SWEEP")) return false;
   if (!dense_derivs_applicable(h, m) || h->precond == QGD_PRECOND_LU || h->Nc < 1) return false;
   smem = (size_t)(m + 1) * 8 * (N2 + 4) * 8 + extra_smem;
-  if (smem + 512 > h->prop.sharedMemPerBlockOptin) return false;
+  if (smem + 1024 > h->prop.sharedMemPerBlockOptin) return false;
   if ((size_t)a.B * (h->nsteps + 1) > 65535) return false;  // grid.y of the operator combination
   const size_t nn = (size_t)N * N, levels = (size_t)a.B * (h->nsteps + 1);
   const size_t comb_bytes = levels * m * 2 * nn * 8;
@@ -766,7 +881,7 @@ bool prepare_dense_sweep(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs& a, 
     CUDA_CHECK(cudaGetLastError());
     h->stats.kernel_launches++;
   }
-  const int groups = (h->ncol + 7) / 8;
+  const int groups = (ncols + 7) / 8;
   grid = std::max(1, std::min(a.B * groups, h->prop.multiProcessorCount));
   const size_t slots = (size_t)grid * 8;
   a.v_stride = (size_t)(N2 + 1) * N2;
@@ -792,7 +907,7 @@ bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs&
   qgd::DenseSweepArgs ds{};
   int grid = 0;
   size_t smem = 0;
-  if (!prepare_dense_sweep(h, d, a, ds, grid, smem, 0)) return false;
+  if (!prepare_dense_sweep(h, d, a, ds, grid, smem, 0, h->ncol)) return false;
   switch (d.m) {
     case 1: launch_forward_dense_t<1>(h, d, a, ds, grid, smem); break;
     case 2: launch_forward_dense_t<2>(h, d, a, ds, grid, smem); break;
@@ -813,7 +928,7 @@ bool try_backward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs
   int grid = 0;
   size_t smem = 0;
   const size_t G = (size_t)2 * d.m * h->Nc * 8;
-  if (!prepare_dense_sweep(h, d, a, ds, grid, smem, (size_t)(h->N / 32 + 1) * G * 8)) return false;
+  if (!prepare_dense_sweep(h, d, a, ds, grid, smem, (size_t)(h->N / 32 + 1) * G * 8, h->ncol)) return false;
   switch (d.m) {
     case 1: launch_backward_dense_t<1>(h, d, a, ds, grid, smem); break;
     case 2: launch_backward_dense_t<2>(h, d, a, ds, grid, smem); break;
@@ -825,3 +940,24 @@ bool try_backward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs
   h->stats.fast_path_launches++;
   return true;
 }
+
+// Infidelity + terminal condition of a dense problem (k_terminal_dense): all nic columns, 8 per CTA.
+bool try_terminal_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a_in) {
+  if (getenv("QGD_DENSE_TERMINAL_GENERIC")) return false;  // one warp per control vector (k_terminal)
+  const int seq = getenv("QGD_DENSE_TERMINAL_PARALLEL") ? 0 : 1;
+  qgd::SweepArgs a = a_in;
+  qgd::DenseSweepArgs ds{};
+  int grid = 0;
+  size_t smem = 0;
+  if (!prepare_dense_sweep(h, d, a, ds, grid, smem, 0, seq ? 1 : h->nic)) return false;
+  switch (d.m) {
+    case 1: launch_terminal_dense_t<1>(h, d, a, ds, grid, smem, seq); break;
+    case 2: launch_terminal_dense_t<2>(h, d, a, ds, grid, smem, seq); break;
+    case 3: launch_terminal_dense_t<3>(h, d, a, ds, grid, smem, seq); break;
+    case 4: launch_terminal_dense_t<4>(h, d, a, ds, grid, smem, seq); break;
+    case 5: launch_terminal_dense_t<5>(h, d, a, ds, grid, smem, seq); break;
+    default: launch_terminal_dense_t<6>(h, d, a, ds, grid, smem, seq); break;
+  }
+  return true;
+}
+

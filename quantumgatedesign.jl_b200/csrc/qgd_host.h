@@ -120,3 +120,4 @@ bool dense_derivs_applicable(const qgd_handle* h, int m);
 void launch_derivs_dense(qgd_handle* h, int m, double* d_uv, int ncols, const double* d_cv, int adjoint);
 bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a);
 bool try_backward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a);
+bool try_terminal_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a);
