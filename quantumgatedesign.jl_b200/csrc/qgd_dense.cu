@@ -203,20 +203,42 @@ __device__ __forceinline__ double dense_dot(const double* a, const double* b, in
   return warp_sum(s);
 }
 
-// DiagonalHamiltonianPreconditioner (src/preconditioners.jl:108-126) on a vector in shared memory
+// Left preconditioner on a vector in shared memory: DiagonalHamiltonianPreconditioner (src/preconditioners.jl:108-126) or
+// LUPreconditioner (:44-76) applied as the explicit inverse, one mat-vec from L2 per column in the order of precond_apply
+// (qgd_warp.cuh).  Lane l owns the elements l + 32 e.
 __device__ __forceinline__ void dense_precond(const QgdDevProb& d, double* w, int lane, int dir) {
-  if (d.precond != QGD_PRECOND_DIAGONAL) return;
-  const int N = d.N;
-  const double* pd = reinterpret_cast<const double*>(d.blob + d.lay.off_pre[dir]);
-  const double* dg = pd; const double* up = pd + d.N2; const double* ratio = up + N; const double* den = ratio + N;
-  for (int r = lane; r < N; r += 32) {
-    double xv = w[N + r] - w[r] * ratio[r];
-    xv = xv / den[r];
-    double xu = w[r] - up[r] * xv;
-    xu = xu / dg[r];
-    w[r] = xu; w[N + r] = xv;
+  const int N = d.N, N2 = d.N2;
+  if (d.precond == QGD_PRECOND_DIAGONAL) {
+    const double* pd = reinterpret_cast<const double*>(d.blob + d.lay.off_pre[dir]);
+    const double* dg = pd; const double* up = pd + N2; const double* ratio = up + N; const double* den = ratio + N;
+    for (int r = lane; r < N; r += 32) {
+      double xv = w[N + r] - w[r] * ratio[r];
+      xv = xv / den[r];
+      double xu = w[r] - up[r] * xv;
+      xu = xu / dg[r];
+      w[r] = xu; w[N + r] = xv;
+    }
+    __syncwarp();
+  } else if (d.precond == QGD_PRECOND_LU) {
+    const double* Mi = d.minv[dir] + lane;  // [2N][2N] column-major
+    double acc[16];                         // 2N <= 512
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+    __syncwarp();
+#pragma unroll 2
+    for (int c = 0; c < N2; ++c) {
+      const double xc = w[c];
+      const double* mc = Mi + (size_t)N2 * c;
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (32 * e < N2) acc[e] = fma(__ldg(mc + 32 * e), xc, acc[e]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (32 * e < N2) w[lane + 32 * e] = acc[e];
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // GMRES bookkeeping of the 8 columns of a CTA (shared memory; lane 0 of the owning warp writes)
@@ -860,7 +882,7 @@ bool prepare_dense_sweep(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs& a, 
                          size_t extra_smem, int ncols) {
   const int m = d.m, N = h->N, N2 = h->N2;
   if (getenv("QGD_DISABLE_DENSE_SWEEP")) return false;
-  if (!dense_derivs_applicable(h, m) || h->precond == QGD_PRECOND_LU || h->Nc < 1) return false;
+  if (!dense_derivs_applicable(h, m) || h->Nc < 1) return false;
   smem = (size_t)(m + 1) * 8 * (N2 + 4) * 8 + extra_smem;
   if (smem + 1024 > h->prop.sharedMemPerBlockOptin) return false;
   if ((size_t)a.B * (h->nsteps + 1) > 65535) return false;  // grid.y of the operator combination
@@ -900,7 +922,7 @@ bool prepare_dense_sweep(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs& a, 
 }  // namespace
 
 // Forward sweep of a dense problem on the tensor-core contraction (k_forward_dense).  false: not applicable (sparse or
-// register-operator problem, LU preconditioner, level count not a multiple of 32, the per-level operators of the whole
+// register-operator problem, level count not a multiple of 32, the per-level operators of the whole
 // time grid do not fit the device memory) -- the caller then uses the generic kernels.
 bool try_forward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a_in) {
   qgd::SweepArgs a = a_in;

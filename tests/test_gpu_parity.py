@@ -508,13 +508,15 @@ def test_dense_tensor_core_derivatives_vs_oracle(q, O, N, order, ncols):
 
 
 @pytest.mark.parametrize("N,nic,order,nsteps,precond", [(32, 11, 10, 6, "identity"), (64, 8, 8, 5, "diagonal"),
-                                                        (64, 3, 4, 7, "identity"), (256, 9, 10, 3, "identity")])
+                                                        (64, 3, 4, 7, "identity"), (256, 9, 10, 3, "identity"),
+                                                        (64, 5, 6, 4, "lu")])
 def test_dense_forward_sweep_tensor_core_vs_oracle(q, O, N, nic, order, nsteps, precond):
     """eval_forward! (src/forward_evolution.jl:88-245) for dense operators with every operator application -- explicit
     Taylor columns and GMRES matvecs -- as the CTA-wide FP64 tensor-core contraction (k_forward_dense): history, final
     state and GMRES iteration counts vs the oracle; ragged column groups (nic not a multiple of 8); two control vectors
     in one launch; identical iteration counts to the generic kernels."""
-    ptype = {"identity": q.IdentityPreconditioner, "diagonal": q.DiagonalHamiltonianPreconditioner}[precond]
+    ptype = {"identity": q.IdentityPreconditioner, "diagonal": q.DiagonalHamiltonianPreconditioner,
+             "lu": q.LUPreconditioner}[precond]
     prob, controls, pcof, target, _ = q.configs.dense_random(N=N, nic=nic, Nc=3, nsteps=nsteps, order=order, gmres_tol=1e-13,
                                                              dt_norm=0.5, preconditioner_type=ptype)
     h = q.Handle(prob, controls)
@@ -552,12 +554,14 @@ def test_dense_forward_sweep_save_every(q, O):
 
 
 @pytest.mark.parametrize("N,nic,order,nsteps,precond,guard", [(32, 11, 10, 5, "identity", True), (64, 8, 8, 4, "diagonal", False),
-                                                              (64, 3, 4, 6, "identity", True), (32, 8, 2, 5, "identity", False)])
+                                                              (64, 3, 4, 6, "identity", True), (32, 8, 2, 5, "identity", False),
+                                                              (32, 9, 6, 4, "lu", True)])
 def test_dense_adjoint_sweep_tensor_core_vs_oracle(q, O, N, nic, order, nsteps, precond, guard):
     """discrete_adjoint! for dense operators with both sweeps on the FP64 tensor cores (k_forward_dense, k_backward_dense):
     gradient, infidelity, guard penalty, lambda and iteration counts vs the oracle and vs the generic kernels; ragged
     column groups, a dense random guard projector (guard forcing in the adjoint right-hand side), two control vectors."""
-    ptype = {"identity": q.IdentityPreconditioner, "diagonal": q.DiagonalHamiltonianPreconditioner}[precond]
+    ptype = {"identity": q.IdentityPreconditioner, "diagonal": q.DiagonalHamiltonianPreconditioner,
+             "lu": q.LUPreconditioner}[precond]
     prob, controls, pcof, target, _ = q.configs.dense_random(N=N, nic=nic, Nc=3, nsteps=nsteps, order=order, gmres_tol=1e-13,
                                                              dt_norm=0.5, preconditioner_type=ptype)
     if guard:  # diagonal 0/1 projector on the upper quarter of the levels, as guard_projector builds it
