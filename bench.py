@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=int(os.environ.get("QGD_CPU_SAMPLE_STEPS", "550")),
                     help="time steps of the C2 problem the CPU baseline integrates per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2: the metric's CNOT3 order-8 workload (default); c4: the dense 4-qudit x 4-level shape "
+                         "(N=256, 256 columns, order 10, 1000 steps) on the FP64 tensor-core sweeps, --batch control vectors per GPU")
     return ap.parse_args()
 
 
@@ -381,10 +384,100 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+
+# ----------------------------------------------------------------------------------------------------
+# C4: dense Hamiltonian on the FP64 tensor-core sweeps (BASELINE.json configs[3]; not the headline metric's workload)
+# ----------------------------------------------------------------------------------------------------
+DMMA_PEAK_TFLOPS = 37.1  # measured DMMA.8x8x4 issue rate on B200, 72.5 warp-instr/ns x 512 flop (profiles/r01_microbench.txt)
+
+
+def run_c4(args):
+    import torch
+
+    q = load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nsteps = 1000 if args.nsteps == 550 else args.nsteps
+    B = 4 if args.batch == 592 else args.batch
+    prob, controls, pcof, target, order = q.configs.dense_random(N=256, nic=256, Nc=4, nsteps=nsteps, order=10, gmres_tol=1e-12,
+                                                                 dt_norm=1.0, n_basis=20, degree=8)
+    m = order // 2
+    rng = np.random.default_rng(100 + rank)  # control vectors shard over the ranks: no data-path collective
+    pcs = np.asfortranarray(np.stack([pcof if (rank == 0 and b == 0) else rng.random(len(pcof)) - 0.5 for b in range(B)], axis=1))
+    tgt = q.complex_to_real(target)
+    h = q.Handle(prob, controls, device=local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        h.discrete_adjoint(pcs, tgt, order=order)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches, iters = 0.0, 0, None
+    for k in range(args.steps):  # through the host C ABI: pcof H2D, gradient / infidelity / guard D2H every step
+        out = h.discrete_adjoint(pcs, tgt, order=order, want_iters=(k == args.steps - 1))
+        st = h.stats()
+        dev_ms += st["last_total_ms"]; launches += st["kernel_launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    itf, ita = out["iters_fwd"], out["iters_adj"]
+    evals = (2 * nsteps + 1) * 256 * B + itf.sum() + (3 * nsteps - 1) * 256 * B + ita.sum()
+    flops = 8.0 * 256 ** 2 * (m * (m + 1) / 2) * float(evals)  # K_d, S_d pre-combined: 8 N^2 per application and column
+    t = torch.tensor([wall, dev_ms * 1e-3], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, dev_s = float(t[0]), float(t[1])
+    if rank == 0:
+        st = h.stats()
+        line = {
+            "metric": "discrete-adjoint gradient evals/sec, dense N=256 order-10 Hermite (C4)", "value": world * B * args.steps / dev_s,
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4 dense random N=256 nic=256 Nc=4 order 10 nsteps={nsteps} P={len(pcof)} gmres_tol=1e-12",
+                       "batch_per_gpu": B, "sharding": "pcof" if world > 1 else "none",
+                       "l2": "inputs larger than L2 (per-level operators + history of one step >> 126 MB)"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": int(st["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(st["d2h_bytes"])},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "k_forward_dense + k_backward_dense (FP64 DMMA)",
+                         "achieved": flops / 1e12 / ((st["last_forward_ms"] + st["last_backward_ms"]) * 1e-3), "peak": DMMA_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": flops / 1e12 / ((st["last_forward_ms"] + st["last_backward_ms"]) * 1e-3) / DMMA_PEAK_TFLOPS,
+                         "traffic": None, "peak_source": "FP64 DMMA.8x8x4 issue-rate micro-benchmark (profiles/r01_microbench.txt); MEASURED_PEAKS.json has no FP64 figure",
+                         "algorithmic_flops_per_step": flops},
+            "kernel_ms": {"k_forward_dense": st["last_forward_ms"], "k_backward_dense": st["last_backward_ms"], "device_total": st["last_total_ms"]},
+            "gmres_iterations_per_step_and_column": {"forward": float(itf.mean()), "backward": float(ita.mean())},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_b200(args)
 
