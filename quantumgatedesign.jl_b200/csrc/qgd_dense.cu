@@ -13,8 +13,13 @@
 //                     shared memory, transposed and padded ([column][2N + 4]) so that the B-fragment loads are
 //                     bank-conflict free; accumulators (4 row tiles x (u, v) x 2) stay in registers across the pair sum.
 //
-// This is the building block of the dense (C4) sweep: the generic sweep kernels reach 0.4 TFLOP/s on that shape
-// (profiles/r01_c4_generic.json); qgd_compute_derivatives routes dense problems with N a multiple of 32 here.
+//   k_forward_dense / k_terminal_dense / k_backward_dense   the sweeps of a gradient evaluation around that contraction
+//                     (eval_forward!, compute_terminal_condition, eval_adjoint! + accumulate_gradient!): 8 columns per
+//                     CTA in lockstep, per-level pre-combined operators (k_dense_combine_levels), GMRES vector work per
+//                     warp (one warp per column), gradient inner products as contractions with the raw control operators.
+//
+// The generic sweep kernels reach 0.4 TFLOP/s on the C4 shape (profiles/r01_c4_generic.json), these 17 TFLOP/s;
+// qgd_compute_derivatives, qgd_eval_forward and qgd_discrete_adjoint* route dense problems with N a multiple of 32 here.
 #include "qgd_host.h"
 #include "qgd_kernels.cuh"
 
@@ -177,6 +182,7 @@ struct DenseSweepArgs {
   const double* comb;  // [B][nsteps+1][M][2][N][N]
   double* xs;          // [grid][8][2N]  state / GMRES iterate
   double* bs;          // [grid][8][2N]  right-hand side
+  double* xp;          // [grid][8][2N]  adjoint sweep: lambda_{n+1} kept beside lambda_n
   double* aux;         // [grid][8][3][2N+2]  Hessenberg column, null vector, least-squares rhs
 };
 
@@ -567,14 +573,19 @@ __global__ void __launch_bounds__(256, 1) k_backward_dense(const __grid_constant
   const size_t slot_sz = (size_t)N2 * (M + 1), tab_stride = (size_t)2 * (M + 1) * P;
   const size_t hist_col_stride = slot_sz * Nt;
 
-  // what_j = alpha_j lambda for the owned columns; zero the gradient slot of this warp
-  auto fill_tiles = [&](const double* alpha, double sign) {
+  // what_j = s1 al1_j x1 (+ s2 al2_j x2) for the owned columns; zero the gradient slot of this warp
+  auto fill_tiles = [&](const double* al1, double s1, const double* base1, const double* al2, double s2, const double* base2) {
     for (int col = warp; col < 8; col += nwarps) {
-      const double* X = ds.xs + ((size_t)blockIdx.x * 8 + col) * N2;
+      const double* X1 = base1 + ((size_t)blockIdx.x * 8 + col) * N2;
+      const double* X2 = base2 ? base2 + ((size_t)blockIdx.x * 8 + col) * N2 : nullptr;
       for (int r = lane; r < N2; r += 32) {
-        const double x = X[r];
+        const double x1 = X1[r], x2 = X2 ? X2[r] : 0.0;
 #pragma unroll
-        for (int j = 0; j <= M; ++j) Wt[((size_t)j * 8 + col) * S + r] = sign * alpha[j] * x;
+        for (int j = 0; j <= M; ++j) {
+          double t = (s1 * al1[j]) * x1;
+          if (X2) t = fma(s2 * al2[j], x2, t);
+          Wt[((size_t)j * 8 + col) * S + r] = t;
+        }
       }
     }
     for (int i = lane; i < G; i += 32) gp[i] = 0.0;
@@ -631,23 +642,31 @@ __global__ void __launch_bounds__(256, 1) k_backward_dense(const __grid_constant
       }
     }
     __syncwarp();
+    // The gradient is linear in the tiles of the reverse sweep, so the two sweeps of a time level L -- the implicit side of
+    // step L-1 (alpha_j = -c_j (-dt)^j, lambda_L) and the explicit side of step L (alpha_j = c_j dt^j, lambda_{L+1}) -- run
+    // as ONE sweep over what_j = c_j dt^j lambda_{L+1} - c_j (-dt)^j lambda_L once lambda_L is known: per step one plain
+    // sweep (the right-hand side R(t_n)^T lambda_{n+1}) and one gradient sweep instead of two gradient sweeps.
+    auto grad_sweep = [&](int level) {
+      __syncthreads();
+      dense_reverse<M, true>(comb_b + (size_t)level * lvl, N, Wt, S, ops, Nc, hist_b + slot_sz * level, hist_col_stride, ncv, gp);
+      reduce_g();
+      __syncthreads();
+      accumulate(b, c0, d.table + (size_t)level * tab_stride);
+    };
+    fill_tiles(d.a_lhs, -1.0, ds.xs, nullptr, 0.0, nullptr);  // level N: implicit side only
+    grad_sweep(d.nsteps);
 #pragma unroll 1
     for (int n = d.nsteps - 1; n >= 0; --n) {
-      // ---- implicit side: time level n+1, alpha_j = -c_j (-dt)^j
-      fill_tiles(d.a_lhs, -1.0);
+      if (n == 0) {  // level 0: explicit side only, no solve
+        fill_tiles(d.a_rhs, 1.0, ds.xs, nullptr, 0.0, nullptr);
+        grad_sweep(0);
+        __syncthreads();
+        break;
+      }
+      // ---- explicit side: what_0 = R(t_n)^T lambda_{n+1}
+      fill_tiles(d.a_rhs, 1.0, ds.xs, nullptr, 0.0, nullptr);
       __syncthreads();
-      dense_reverse<M, true>(comb_b + (size_t)(n + 1) * lvl, N, Wt, S, ops, Nc, hist_b + slot_sz * (n + 1), hist_col_stride, ncv, gp);
-      reduce_g();
-      __syncthreads();
-      accumulate(b, c0, d.table + (size_t)(n + 1) * tab_stride);
-      // ---- explicit side: time level n, alpha_j = c_j dt^j; what_0 = R(t_n)^T lambda_{n+1}
-      fill_tiles(d.a_rhs, 1.0);
-      __syncthreads();
-      dense_reverse<M, true>(comb_b + (size_t)n * lvl, N, Wt, S, ops, Nc, hist_b + slot_sz * n, hist_col_stride, ncv, gp);
-      reduce_g();
-      __syncthreads();
-      accumulate(b, c0, d.table + (size_t)n * tab_stride);
-      if (n == 0) { __syncthreads(); break; }
+      dense_reverse<M, false>(comb_b + (size_t)n * lvl, N, Wt, S, nullptr, 0, nullptr, 0, 0, nullptr);
       // ---- lambda_n: LHS(t_n)^T lambda_n = R(t_n)^T lambda_{n+1} + f_n, x0 = lambda_{n+1} (forward_evolution.jl:450)
       for (int col = warp; col < 8; col += nwarps) {
         const int cl = c0 + col;
@@ -664,7 +683,8 @@ __global__ void __launch_bounds__(256, 1) k_backward_dense(const __grid_constant
             for (int s = 0; s < d.lay.LW; ++s) g = fma(wval[(size_t)s * N2 + r], __ldg(wn + wcol[(size_t)s * N2 + r]), g);
           Bv[r] = fma(fsc, g, Wt[(size_t)col * S + r]);
         }
-        for (int r = lane; r < N2; r += 32) dense_publish<M, true>(d, Wt, S, col, r, X[r]);
+        double* Xp = ds.xp + ((size_t)blockIdx.x * 8 + col) * N2;
+        for (int r = lane; r < N2; r += 32) { const double x = X[r]; Xp[r] = x; dense_publish<M, true>(d, Wt, S, col, r, x); }
         if (lane == 0) { cs.state[col] = valid ? DCOL_RESID0 : DCOL_DONE; cs.it[col] = 0; cs.k[col] = 1; }
       }
       __syncthreads();
@@ -692,6 +712,9 @@ __global__ void __launch_bounds__(256, 1) k_backward_dense(const __grid_constant
         }
         if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = cs.it[col];
       }
+      // ---- gradient of time level n: explicit side with lambda_{n+1}, implicit side with lambda_n, one sweep
+      fill_tiles(d.a_rhs, 1.0, ds.xp, d.a_lhs, -1.0, ds.xs);
+      grad_sweep(n);
     }
   }
 }
@@ -912,11 +935,12 @@ bool prepare_dense_sweep(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs& a, 
   h->d_H.reserve(slots * a.h_stride * 8);
   a.Vws = h->d_V.as<double>();
   a.Hws = h->d_H.as<double>();
-  h->d_dense_ws.reserve(slots * (2 * (size_t)N2 + 3 * ((size_t)N2 + 2)) * 8);
+  h->d_dense_ws.reserve(slots * (3 * (size_t)N2 + 3 * ((size_t)N2 + 2)) * 8);
   ds.comb = h->d_comb.as<double>();
   ds.xs = h->d_dense_ws.as<double>();
   ds.bs = ds.xs + slots * N2;
-  ds.aux = ds.bs + slots * N2;
+  ds.xp = ds.bs + slots * N2;
+  ds.aux = ds.xp + slots * N2;
   return true;
 }
 }  // namespace
