@@ -625,3 +625,38 @@ def test_dense_column_sharding_two_phase(q):
         assert abs(infid[0] - full["infidelity"][0]) <= 1e-13
     assert rel(grad[:, 0], full["grad"][:, 0]) < 1e-11
 
+
+def test_dense_sweeps_edge_cases(q, O):
+    """Dense tensor-core sweeps at the smallest shapes: one time step, one column, order 2; GMRES to the cap with zero
+    tolerance (2N iterations, least-squares solution at the cap); history_precomputed on the resident history."""
+    prob, controls, pcof, target, _ = q.configs.dense_random(N=32, nic=1, Nc=1, nsteps=1, order=2, gmres_tol=1e-14, dt_norm=0.4)
+    for order in (2, 4):
+        h = q.Handle(prob, controls)
+        out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_history=True, want_iters=True)
+        assert h.stats()["fast_path_launches"] == 2
+        ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+        assert rel(out["history"][..., 0], ref["history"]) < RTOL
+        assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+        assert np.abs(out["iters_fwd"][:, :, 0] - ref["iters_fwd"]).max() <= 1
+        h.close()
+    prob, controls, pcof, target, order = q.configs.dense_random(N=32, nic=3, Nc=2, nsteps=3, order=4, gmres_tol=0.0, dt_norm=0.5)
+    h = q.Handle(prob, controls)
+    tgt = q.complex_to_real(target)
+    out = h.discrete_adjoint(pcof, tgt, order=order, want_iters=True)
+    assert h.stats()["fast_path_launches"] == 2
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    n2 = prob.real_system_size
+    assert np.all(ref["iters_fwd"] == n2) and np.all(out["iters_fwd"][:, :, 0] == n2)
+    assert np.all(out["iters_adj"][1:, :, 0] == n2)
+    assert rel(out["grad"][:, 0], ref["grad"]) < 1e-8
+    h.close()
+    prob, controls, pcof, target, order = q.configs.dense_random(N=32, nic=9, Nc=2, nsteps=4, order=6, gmres_tol=1e-13, dt_norm=0.5)
+    h = q.Handle(prob, controls)
+    tgt = q.complex_to_real(target)
+    one = h.discrete_adjoint(pcof, tgt, order=order)
+    h.eval_forward(pcof, order=order, want_history=False, want_iters=False)
+    two = h.discrete_adjoint(pcof, tgt, order=order, history_precomputed=True)
+    assert h.stats()["fast_path_launches"] == 1  # only the adjoint sweep ran
+    assert np.array_equal(one["grad"], two["grad"]) and np.array_equal(one["infidelity"], two["infidelity"])
+    h.close()
+
