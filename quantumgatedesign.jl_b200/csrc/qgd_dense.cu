@@ -48,22 +48,30 @@ __global__ void k_dense_combine(const double* __restrict__ ops /*[Nc+1][2][N][N]
 // ([column][S] layout), A_d = [S_d K_d; -K_d S_d] streamed from L2.
 __device__ __forceinline__ void dense_pair(const double* __restrict__ comb, int d, int N, int r0, int lane, const double* B, int S,
                                            double (&aU)[4][2], double (&aV)[4][2]) {
+  // k mapping of a step of 8 columns: lane ak supplies columns k0 + 2 ak (first DMMA) and k0 + 2 ak + 1 (second DMMA) of A
+  // and the same rows of B, so both operands come in with 16-byte loads (the sum over k does not care about the order)
   const int ar = lane >> 2, ak = lane & 3;
   const size_t nn = (size_t)N * N;
-  const double* Kd = comb + ((size_t)d * 2 + 0) * nn + (size_t)(r0 + ar) * N + ak;
-  const double* Sd = comb + ((size_t)d * 2 + 1) * nn + (size_t)(r0 + ar) * N + ak;
-  const double* Bu = B + (size_t)ar * S + ak;
+  const double* Kd = comb + ((size_t)d * 2 + 0) * nn + (size_t)(r0 + ar) * N + 2 * ak;
+  const double* Sd = comb + ((size_t)d * 2 + 1) * nn + (size_t)(r0 + ar) * N + 2 * ak;
+  const double* Bu = B + (size_t)ar * S + 2 * ak;
   const double* Bv = Bu + N;
-#pragma unroll 4
-  for (int k0 = 0; k0 < N; k0 += 4) {
-    const double bu = Bu[k0], bv = Bv[k0], nbu = -bu;
+#pragma unroll 2
+  for (int k0 = 0; k0 < N; k0 += 8) {
+    const double2 bu = *reinterpret_cast<const double2*>(Bu + k0), bv = *reinterpret_cast<const double2*>(Bv + k0);
+    const double nbx = -bu.x, nby = -bu.y;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const double aS = __ldg(Sd + (size_t)8 * t * N + k0), aK = __ldg(Kd + (size_t)8 * t * N + k0);
-      dmma884_acc(aU[t][0], aU[t][1], aS, bu);
-      dmma884_acc(aU[t][0], aU[t][1], aK, bv);
-      dmma884_acc(aV[t][0], aV[t][1], aS, bv);
-      dmma884_acc(aV[t][0], aV[t][1], aK, nbu);
+      const double2 aS = __ldg(reinterpret_cast<const double2*>(Sd + (size_t)8 * t * N + k0));
+      const double2 aK = __ldg(reinterpret_cast<const double2*>(Kd + (size_t)8 * t * N + k0));
+      dmma884_acc(aU[t][0], aU[t][1], aS.x, bu.x);
+      dmma884_acc(aU[t][0], aU[t][1], aK.x, bv.x);
+      dmma884_acc(aV[t][0], aV[t][1], aS.x, bv.x);
+      dmma884_acc(aV[t][0], aV[t][1], aK.x, nbx);
+      dmma884_acc(aU[t][0], aU[t][1], aS.y, bu.y);
+      dmma884_acc(aU[t][0], aU[t][1], aK.y, bv.y);
+      dmma884_acc(aV[t][0], aV[t][1], aS.y, bv.y);
+      dmma884_acc(aV[t][0], aV[t][1], aK.y, nby);
     }
   }
 }
@@ -452,20 +460,25 @@ __device__ __forceinline__ void dense_raw4(const double* __restrict__ Kk, const 
                                            const double* B, int S, double (&zKu)[4][2], double (&zKv)[4][2], double (&zSu)[4][2],
                                            double (&zSv)[4][2]) {
   const int ar = lane >> 2, ak = lane & 3;
-  const double* Kp = Kk + (size_t)(r0 + ar) * N + ak;
-  const double* Sp = Sk + (size_t)(r0 + ar) * N + ak;
-  const double* Bu = B + (size_t)ar * S + ak;
+  const double* Kp = Kk + (size_t)(r0 + ar) * N + 2 * ak;  // k mapping and 16-byte loads as in dense_pair
+  const double* Sp = Sk + (size_t)(r0 + ar) * N + 2 * ak;
+  const double* Bu = B + (size_t)ar * S + 2 * ak;
   const double* Bv = Bu + N;
-#pragma unroll 2
-  for (int k0 = 0; k0 < N; k0 += 4) {
-    const double bu = Bu[k0], bv = Bv[k0];
+#pragma unroll 1
+  for (int k0 = 0; k0 < N; k0 += 8) {
+    const double2 bu = *reinterpret_cast<const double2*>(Bu + k0), bv = *reinterpret_cast<const double2*>(Bv + k0);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const double aS = __ldg(Sp + (size_t)8 * t * N + k0), aK = __ldg(Kp + (size_t)8 * t * N + k0);
-      dmma884_acc(zSu[t][0], zSu[t][1], aS, bu);
-      dmma884_acc(zKv[t][0], zKv[t][1], aK, bv);
-      dmma884_acc(zSv[t][0], zSv[t][1], aS, bv);
-      dmma884_acc(zKu[t][0], zKu[t][1], aK, bu);
+      const double2 aS = __ldg(reinterpret_cast<const double2*>(Sp + (size_t)8 * t * N + k0));
+      const double2 aK = __ldg(reinterpret_cast<const double2*>(Kp + (size_t)8 * t * N + k0));
+      dmma884_acc(zSu[t][0], zSu[t][1], aS.x, bu.x);
+      dmma884_acc(zKv[t][0], zKv[t][1], aK.x, bv.x);
+      dmma884_acc(zSv[t][0], zSv[t][1], aS.x, bv.x);
+      dmma884_acc(zKu[t][0], zKu[t][1], aK.x, bu.x);
+      dmma884_acc(zSu[t][0], zSu[t][1], aS.y, bu.y);
+      dmma884_acc(zKv[t][0], zKv[t][1], aK.y, bv.y);
+      dmma884_acc(zSv[t][0], zSv[t][1], aS.y, bv.y);
+      dmma884_acc(zKu[t][0], zKu[t][1], aK.y, bu.y);
     }
   }
 }
