@@ -118,6 +118,34 @@ const char *qgd_last_error(void);
 int qgd_set_nsteps(qgd_handle_t *h, int64_t nsteps);
 int qgd_set_gmres_tolerances(qgd_handle_t *h, double abstol, double reltol);
 
+/* Behaviour switches of a handle (they replace the environment variables of the first round; nothing in the library
+ * reads the environment).  Unknown keys return QGD_EINVAL.  Changing an option invalidates the resident history. */
+#define QGD_OPT_STRICT_MGS 1            /* 1: strict modified Gram-Schmidt in the register-operator sweeps, the
+                                         * orthogonalisation of IterativeSolvers' ModifiedGramSchmidt one projection at a
+                                         * time (iteration counts equal the reference algorithm's, tests assert equality);
+                                         * 0 (default): coefficients of 32 basis vectors at a time from the same vector
+                                         * (classical inside a block, modified across blocks)      */
+#define QGD_OPT_DISABLE_FAST 2          /* 1: never take the register-operator sweeps (qgd_fast.cuh)                    */
+#define QGD_OPT_DISABLE_DENSE_SWEEP 3   /* 1: never take the FP64 tensor-core sweeps (qgd_dense.cu)                     */
+#define QGD_OPT_DISABLE_DENSE_DMMA 4    /* 1: qgd_compute_derivatives never takes the tensor-core contraction           */
+#define QGD_OPT_DENSE_TERMINAL 5        /* dense terminal condition: 0 sequential columns with the reference's carried
+                                         * initial guess (default), 1 all columns in parallel from a zero guess,
+                                         * 2 the generic one-warp kernel                                                */
+#define QGD_OPT_DISABLE_TMEM 6          /* 1: no tensor-memory tier for the Krylov basis                                */
+#define QGD_OPT_SEG_STEPS 7             /* time steps per work-queue ticket (0: automatic, about nsteps / 24)           */
+#define QGD_OPT_L2_PERSIST 8            /* 1: persisting L2 access-policy window over the Krylov workspace              */
+#define QGD_OPT_LATENCY_WARPS 9         /* warps per CTA of the register-operator sweeps (0: automatic)                 */
+#define QGD_OPT_TERMINAL_EXCHANGE 10    /* column sharding over GPUs, exchange between the sweeps: 0 (default) the final
+                                         * states of all columns (2N*nic doubles per control vector), every rank then
+                                         * solves the terminal condition of all columns in the reference's order with its
+                                         * carried initial guess -- results equal the single-GPU ones; 1 only the two
+                                         * scalars dot(psi,R), dot(psi,T) per control vector, every rank solves its own
+                                         * columns (the first one from a zero guess: lambda_N moves by the GMRES
+                                         * tolerance; sparse problems only)                                             */
+#define QGD_OPT_MAX 10
+int qgd_set_option(qgd_handle_t *h, int32_t key, int64_t value);
+int qgd_get_option(qgd_handle_t *h, int32_t key, int64_t *value);
+
 /* Restrict this handle to the initial-condition columns [col_begin, col_begin+col_count)
  * (multi-GPU column sharding: one process per GPU each owning a contiguous block, the
  * GPU counterpart of `Threads.@threads for initial_condition_index`,
@@ -193,6 +221,47 @@ int qgd_discrete_adjoint_device(qgd_handle_t *h, const double *d_pcof, int64_t n
                                 const double *d_target, int32_t order, double *d_grad,
                                 double *d_infidelity, double *d_guard_penalty, void *stream);
 
+/* Synchronise the handle's stream (and `stream`, if not NULL) and report the device error word of the sweeps: the way
+ * to complete and check an asynchronous qgd_discrete_adjoint_device call. */
+int qgd_synchronize(qgd_handle_t *h, void *stream);
+
+/* ---- multi-GPU inside the library ------------------------------------------------------------------------------------
+ * The reference parallelises over the independent initial-condition columns (Threads.@threads,
+ * src/forward_evolution.jl:48,332); they couple only through dot(final_state, R), dot(final_state, T) of
+ * compute_terminal_condition (src/eval_grad_discrete_adjoint.jl:27-28) and the serial gradient sum (:150-157).  With a
+ * communicator attached, qgd_discrete_adjoint / qgd_discrete_adjoint_device on every participating handle evaluate
+ * the SAME control vectors on their own block of columns and exchange on the device, on the sweep stream: one NCCL
+ * all-reduce between the sweeps (QGD_OPT_TERMINAL_EXCHANGE) and one all-reduce of [grad; guard] at the end; every rank
+ * returns the complete gradient, infidelity and guard penalty.  NCCL is bound at run time (libnccl.so.2).
+ *
+ * (a) one process per GPU: rank 0 calls qgd_comm_get_unique_id, the host program distributes the 128 bytes (MPI,
+ *     torch.distributed, a file ...), every rank calls qgd_comm_init_rank on its handle (collective), which also
+ *     assigns the rank its contiguous column block [rank*nic/n, (rank+1)*nic/n). */
+#define QGD_NCCL_UNIQUE_ID_BYTES 128
+int qgd_comm_set_nccl_library(const char *path); /* optional: path of libnccl.so.2 (default: the loader's search)      */
+int qgd_comm_get_unique_id(unsigned char *id128);
+int qgd_comm_init_rank(qgd_handle_t *h, int32_t n_ranks, int32_t rank, const unsigned char *id128);
+int qgd_comm_finalize(qgd_handle_t *h);           /* back to a single-GPU handle owning all columns                     */
+
+/* (b) one process driving n GPUs (what a Julia session does: `qgd_init_multi_gpu` of SURVEY 8b).  The set owns one
+ *     handle per device and an NCCL communicator over them (ncclCommInitAll).
+ *     shard = QGD_SHARD_COLUMNS: every GPU takes a block of columns of all n_batch control vectors (the exchanges
+ *     above, grouped); QGD_SHARD_CONTROL_VECTORS: every GPU takes a block of the control vectors with all columns, no
+ *     collective (the batched random-pcof sweep).  Host buffers in and out like qgd_discrete_adjoint. */
+typedef struct qgd_multi qgd_multi_t;
+#define QGD_SHARD_COLUMNS 0
+#define QGD_SHARD_CONTROL_VECTORS 1
+int qgd_init_multi_gpu(const qgd_problem_t *prob, int32_t n_gpus, const int32_t *devices /* NULL: 0..n_gpus-1 */,
+                       qgd_multi_t **out);
+int qgd_multi_n_gpus(qgd_multi_t *mg);
+int qgd_multi_handle(qgd_multi_t *mg, int32_t i, qgd_handle_t **out); /* per-device handle, e.g. for qgd_set_option */
+int qgd_multi_set_nsteps(qgd_multi_t *mg, int64_t nsteps);
+int qgd_multi_set_gmres_tolerances(qgd_multi_t *mg, double abstol, double reltol);
+int qgd_multi_discrete_adjoint(qgd_multi_t *mg, const double *pcof, int64_t n_batch, const double *target,
+                               int32_t order, int32_t shard, double *grad, double *infidelity,
+                               double *guard_penalty);
+int qgd_multi_destroy(qgd_multi_t *mg);
+
 /* Two-phase form for column sharding across GPUs: phase 1 runs the forward
  * sweep on the owned columns and returns their final states and guard-penalty partial;
  * the host all-gathers the final states (the only cross-column coupling: <psi,R>, <psi,T>
@@ -236,6 +305,7 @@ typedef struct qgd_stats {
   double last_backward_ms; /* CUDA-event time of the backward sweep kernel */
   double last_total_ms;    /* CUDA-event time of the whole device section  */
   int64_t fast_path_launches; /* sweep launches that took the register-operator kernels (qgd_fast.cuh) */
+  int64_t collectives;        /* NCCL collectives enqueued by the call (multi-GPU)                      */
 } qgd_stats_t;
 int qgd_get_stats(qgd_handle_t *h, qgd_stats_t *out);
 

@@ -2,9 +2,21 @@
 #
 # NOT EXECUTED in this repository's CI: neither the build image nor the GPU box has Julia
 # (SURVEY section 0.10).  The same C ABI is exercised on every run through Python ctypes
-# (quantumgatedesign.jl_b200/_abi.py, tests/).  This file is what a maintainer of the reference
-# would `include` from src/QuantumGateDesign.jl after the existing includes (it needs
+# (quantumgatedesign.jl_b200/_abi.py, tests/) and from plain C (tests/abi_c/abi_smoke.c).  This file is what a
+# maintainer of the reference would `include` from src/QuantumGateDesign.jl after the existing includes (it needs
 # SchrodingerProb, the control types, the preconditioner types and complex_to_real).
+#
+# THE SEAM IS MULTIPLE DISPATCH, no caller changes: `gpu_prob = b200(prob)` returns a SchrodingerProb that shares every
+# array with `prob` and whose preconditioner type parameter is the tag `B200{P}`.  The methods below are more specific
+# than the reference's on exactly that parameter, with the reference's exact signatures
+#     eval_forward!(uv_history, prob, controls, pcof; order, saveEveryNsteps, forcing)      src/forward_evolution.jl:33-37
+#     discrete_adjoint!(grad, history, lambda_history, adjoint_forcing, prob, controls, pcof, target;
+#                       order, cost_type, history_precomputed)                              src/eval_grad_discrete_adjoint.jl:107-115
+#     eval_grad_forced(prob, controls, pcof, target; order, cost_type)                      src/eval_grad_forced.jl:18-26
+# so eval_forward, discrete_adjoint, infidelity, optimize_gate (src/ipopt_optimal_control.jl:257,304), get_histories,
+# estimate_timesteps_per_period ... reach the GPU unchanged when handed `gpu_prob`.  Anything NOT overridden (eval_adjoint!,
+# the finite-difference gradient, plotting) keeps working on the CPU, because B200{P}(prob, order, adjoint) constructs the
+# reference's own preconditioner P.
 #
 # The style follows the reference's own ccall of its Fortran library
 # (src/Controls/FortranBSpline.jl:1, 257-265).
@@ -83,11 +95,33 @@ struct QgdStats
     last_backward_ms::Float64
     last_total_ms::Float64
     fast_path_launches::Int64
+    collectives::Int64
 end
+
+# ---- the dispatch tag -------------------------------------------------------------------------------------
+"""
+    B200{P}
+
+Preconditioner-type tag: a `SchrodingerProb{M,VM,B200{P}}` runs the gradient hot path on the B200 with the reference
+preconditioner `P` (Identity / LU / DiagonalHamiltonian).  As a constructor it builds `P` itself, so CPU code paths
+that were not overridden still get a working preconditioner (protocol of src/preconditioners.jl:1-28).
+"""
+struct B200{P<:AbstractQGDPreconditioner} <: AbstractQGDPreconditioner end
+B200{P}(prob::SchrodingerProb, order::Int, adjoint::Bool=false) where {P} = P(prob, order, adjoint)
+
+"A problem that shares every array with `prob` and dispatches the hot path to the GPU."
+function b200(prob::SchrodingerProb{M,VM,P}) where {M,VM,P}
+    P <: B200 && return prob
+    return SchrodingerProb(prob.system_sym, prob.system_asym, prob.sym_operators, prob.asym_operators, prob.u0, prob.v0,
+                           prob.guard_subspace_projector, prob.tf, prob.nsteps, prob.N_ess_levels,
+                           prob.gmres_abstol, prob.gmres_reltol, B200{P})
+end
+const B200Prob{M,VM,P} = SchrodingerProb{M,VM,B200{P}}
 
 qgd_precond(::Type{IdentityPreconditioner}) = Int32(0)
 qgd_precond(::Type{LUPreconditioner}) = Int32(1)
 qgd_precond(::Type{DiagonalHamiltonianPreconditioner}) = Int32(2)
+qgd_precond(::Type{B200{P}}) where {P} = qgd_precond(P)
 
 function qgd_check(rc::Integer)
     rc == 0 && return nothing
@@ -122,16 +156,31 @@ mutable struct B200Handle
     end
 end
 
-"Forward the reference's mutable knobs (examples/cnot3_optimize_gate.jl:51-55) before each call."
+"Forward the reference's mutable knobs (examples/cnot3_optimize_gate.jl:51-55) before each call.  The C setters are
+no-ops when the value is unchanged, so this does not invalidate a resident history (history_precomputed)."
 function sync_knobs!(h::B200Handle, prob::SchrodingerProb)
     qgd_check(ccall((:qgd_set_nsteps, libqgd), Cint, (Ptr{Cvoid}, Int64), h.ptr, prob.nsteps))
     qgd_check(ccall((:qgd_set_gmres_tolerances, libqgd), Cint, (Ptr{Cvoid}, Float64, Float64),
                     h.ptr, prob.gmres_abstol, prob.gmres_reltol))
 end
 
-const _handles = IdDict{Any,B200Handle}()
+"qgd_set_option (include/qgd_b200.h), e.g. `set_option!(h, 1, 1)` for strict modified Gram-Schmidt."
+set_option!(h::B200Handle, key::Integer, value::Integer) =
+    qgd_check(ccall((:qgd_set_option, libqgd), Cint, (Ptr{Cvoid}, Int32, Int64), h.ptr, key, value))
+
+# What qgd_create reads from a control: type and shape parameters (not the coefficients).
+control_key(c::CarrierControl) = (:carrier, control_key(c.base_control), Tuple(c.carrier_frequencies))
+control_key(c::AbstractControl) = (nameof(typeof(c)), c.N_coeff, c.tf,
+                                   Tuple(getfield(c, f) for f in fieldnames(typeof(c)) if getfield(c, f) isa Integer))
+
+# One handle per (problem object, control descriptors, device).  Weak keys: the handle (and its device memory) goes
+# when the problem does; a different set of controls on the same problem gets its own handle.
+const _handles = WeakKeyDict{Any,Dict{Any,B200Handle}}()
 function b200_handle(prob::SchrodingerProb, controls; device::Integer=-1)
-    h = get!(() -> B200Handle(prob, controls; device=device), _handles, prob)
+    ctrl_list = controls isa AbstractControl ? [controls] : collect(controls)
+    key = (Tuple(control_key(c) for c in ctrl_list), prob.tf, Int(device))
+    per_prob = get!(() -> Dict{Any,B200Handle}(), _handles, prob)
+    h = get!(() -> B200Handle(prob, ctrl_list; device=device), per_prob, key)
     sync_knobs!(h, prob)
     return h
 end
@@ -139,8 +188,21 @@ end
 _ptr_or_null(::Nothing) = Ptr{Float64}(C_NULL)
 _ptr_or_null(::Missing) = Ptr{Float64}(C_NULL)
 _ptr_or_null(A::Array{Float64}) = pointer(A)
+_ptr_or_null(A::AbstractArray{Float64}) = throw(ArgumentError("the B200 path writes into contiguous Array{Float64} buffers (got $(typeof(A)))"))
 
-# ---- eval_forward!  (src/forward_evolution.jl:33-70) ---------------------------------------------------
+# ---- eval_forward!  (src/forward_evolution.jl:33-70): method of the reference's function for tagged problems ----
+function eval_forward!(uv_history::AbstractArray{Float64,4},
+        prob::SchrodingerProb{M1,M2,B200{P}}, controls, pcof::AbstractVector{<:Real};
+        order::Int=2, saveEveryNsteps::Int=1,
+        forcing::Union{AbstractArray{Float64,4},Missing}=missing
+    ) where {M1<:AbstractMatrix{Float64},M2<:AbstractMatrix{Float64},P}
+    hist = uv_history isa Array{Float64,4} ? uv_history : Array{Float64,4}(uv_history)
+    eval_forward_b200!(hist, prob, controls, Vector{Float64}(pcof); order=order, saveEveryNsteps=saveEveryNsteps,
+                       forcing=ismissing(forcing) ? missing : Array{Float64,4}(forcing))
+    hist === uv_history || (uv_history .= hist)
+    return nothing
+end
+
 function eval_forward_b200!(uv_history::Array{Float64,4}, prob::SchrodingerProb, controls,
         pcof::Vector{Float64}; order::Int=2, saveEveryNsteps::Int=1, forcing=missing, device::Integer=-1)
     m = div(order, 2)
@@ -166,6 +228,13 @@ function eval_forward_b200!(uv_history::Array{Float64,4}, prob::SchrodingerProb,
 end
 
 # ---- eval_grad_forced  (src/eval_grad_forced.jl:18-195): P forced solves batched on the device -----------
+function eval_grad_forced(prob::SchrodingerProb{M,VM,B200{P}}, controls, pcof::AbstractVector{Float64},
+        target::AbstractVecOrMat{<:Number}; order::Integer=2, cost_type=:Infidelity, return_forcing=false
+    ) where {M<:AbstractMatrix{Float64},VM<:AbstractVecOrMat{Float64},P}
+    return_forcing && throw(ArgumentError("return_forcing is not available on the B200 path (the forcing of the P forced solves is formed on the fly)"))
+    return eval_grad_forced_b200(prob, controls, Vector{Float64}(pcof), target; order=Int(order), cost_type=cost_type)
+end
+
 function eval_grad_forced_b200(prob::SchrodingerProb, controls, pcof::Vector{Float64}, target::AbstractMatrix{<:Number};
         order::Int=2, cost_type=:Infidelity, device::Integer=-1)
     cost_type == :Infidelity || throw("Invalid cost type: $cost_type")
@@ -213,7 +282,30 @@ function discrete_adjoint_b200_tables(prob::SchrodingerProb, controls, pcof::Vec
     return grad, infid[], guard[]
 end
 
-# ---- discrete_adjoint!  (src/eval_grad_discrete_adjoint.jl:107-160) ------------------------------------
+# ---- discrete_adjoint!  (src/eval_grad_discrete_adjoint.jl:107-160): method of the reference's function ----------
+function discrete_adjoint!(
+        grad::AbstractVector{Float64}, history::AbstractArray{Float64,4},
+        lambda_history::AbstractArray{Float64,4}, adjoint_forcing::AbstractArray{Float64,3},
+        prob::SchrodingerProb{<:AbstractMatrix{Float64},<:AbstractMatrix{Float64},B200{P}},
+        controls, pcof::AbstractVector{<:Real}, target::AbstractMatrix{<:Number};
+        order=2, cost_type=:Infidelity, history_precomputed=false
+    ) where {P}
+    g = grad isa Vector{Float64} ? grad : Vector{Float64}(grad)
+    if any(is_host_control, controls isa AbstractControl ? [controls] : controls)
+        gt, _, _ = discrete_adjoint_b200_tables(prob, controls, Vector{Float64}(pcof), target; order=Int(order))
+        grad .= gt
+        return grad
+    end
+    # history_precomputed: the reference reuses the ARRAY the caller passes; here the history of the previous
+    # eval_forward! / discrete_adjoint! of this (prob, controls) is still on the device and is reused when it belongs to the
+    # same pcof (QGD_ESTATE otherwise, re-raised below) -- the array contents are not uploaded.
+    discrete_adjoint_b200!(g, history_precomputed ? nothing : history, lambda_history, adjoint_forcing, prob, controls,
+                           Vector{Float64}(pcof), target; order=Int(order), cost_type=cost_type,
+                           history_precomputed=Bool(history_precomputed))
+    g === grad || (grad .= g)
+    return grad
+end
+
 function discrete_adjoint_b200!(grad::Vector{Float64}, history, lambda_history, adjoint_forcing,
         prob::SchrodingerProb, controls, pcof::Vector{Float64}, target::AbstractMatrix{<:Number};
         order::Int=2, cost_type=:Infidelity, history_precomputed::Bool=false, device::Integer=-1)
@@ -245,5 +337,43 @@ function discrete_adjoint_b200_batch(prob::SchrodingerProb, controls, pcofs::Mat
          Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
         h.ptr, pcofs, B, R, order, false, grad, infid, guard, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
+    return grad, infid, guard
+end
+
+
+# ---- multi-GPU from one Julia process (qgd_init_multi_gpu): n handles + an NCCL communicator inside the library ----
+mutable struct B200MultiGPU
+    ptr::Ptr{Cvoid}
+    n_gpus::Int
+end
+function B200MultiGPU(prob::SchrodingerProb{M,VM,P}, controls, n_gpus::Integer) where {M,VM,P}
+    ctrl_list = controls isa AbstractControl ? [controls] : collect(controls)
+    u0 = Matrix{Float64}(prob.u0); v0 = Matrix{Float64}(prob.v0)
+    sym = [QgdMatrix(A) for A in prob.sym_operators]; asym = [QgdMatrix(A) for A in prob.asym_operators]
+    cds = [qgd_control(c) for c in ctrl_list]
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve prob u0 v0 sym asym cds ctrl_list begin
+        p = QgdProblem(prob.N_tot_levels, prob.N_ess_levels, prob.N_initial_conditions, prob.N_operators,
+                       QgdMatrix(prob.system_sym), QgdMatrix(prob.system_asym), pointer(sym), pointer(asym),
+                       pointer(u0), pointer(v0), QgdMatrix(prob.guard_subspace_projector),
+                       prob.tf, prob.nsteps, prob.gmres_abstol, prob.gmres_reltol, qgd_precond(P), 0, pointer(cds))
+        qgd_check(ccall((:qgd_init_multi_gpu, libqgd), Cint, (Ref{QgdProblem}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+                        p, n_gpus, C_NULL, out))
+    end
+    mg = B200MultiGPU(out[], n_gpus)
+    finalizer(x -> ccall((:qgd_multi_destroy, libqgd), Cint, (Ptr{Cvoid},), x.ptr), mg)
+    return mg
+end
+
+"`shard = 0`: the columns of every control vector over the GPUs (two NCCL all-reduces per evaluation, on the device);
+`shard = 1`: the control vectors over the GPUs (no collective).  pcofs [P, B] -> (grad [P, B], infidelity [B], guard [B])."
+function discrete_adjoint_multi(mg::B200MultiGPU, pcofs::Matrix{Float64}, target::AbstractMatrix{<:Number};
+        order::Int=2, shard::Integer=0)
+    R = Matrix{Float64}(complex_to_real(target))
+    P, B = size(pcofs)
+    grad = zeros(P, B); infid = zeros(B); guard = zeros(B)
+    qgd_check(ccall((:qgd_multi_discrete_adjoint, libqgd), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        mg.ptr, pcofs, B, R, order, shard, grad, infid, guard))
     return grad, infid, guard
 end

@@ -718,6 +718,11 @@ void givens_algorithm(double f, double g, double& cs, double& sn, double& r) {  
   }
 }
 
+inline int gs_block_experiment() {  // 0 / 1: strict modified Gram-Schmidt (the reference); see Gmres::run
+  static const int b = [] { const char* e = getenv("QGDO_GS_BLOCK"); return e ? atoi(e) : 0; }();
+  return b;
+}
+
 struct Gmres {
   i64 n = 0; int restart = 0; int maxiter = 0;
   double tol = 0, beta = 0;
@@ -806,11 +811,27 @@ struct Gmres {
       double* w = &V[(size_t)n * k];
       A(w, vk);                       // expand!
       if (Pl) Pl->ldiv(w);
+      if (gs_block_experiment() <= 1) {
       for (int i = 0; i < k; ++i) {   // ModifiedGramSchmidt
         const double* col = &V[(size_t)n * i];
         double h = dotv(col, w, n);
         H[i + ldh * (k - 1)] = h;
         for (i64 r = 0; r < n; ++r) w[r] -= h * col[r];
+      }
+      } else {
+        // EXPERIMENT ONLY (QGDO_GS_BLOCK=B, tools/gs_block_experiment.py): classical Gram-Schmidt inside blocks of B
+        // basis vectors, modified across blocks -- the orthogonalisation of the CUDA fast path -- to measure on the CPU
+        // how far the iteration counts move from strict MGS before a block width is adopted on the device.
+        const int B = gs_block_experiment();
+        for (int i0 = 0; i0 < k; i0 += B) {
+          const int i1 = std::min(k, i0 + B);
+          for (int i = i0; i < i1; ++i) H[i + ldh * (k - 1)] = dotv(&V[(size_t)n * i], w, n);
+          for (int i = i0; i < i1; ++i) {
+            const double h = H[i + ldh * (k - 1)];
+            const double* col = &V[(size_t)n * i];
+            for (i64 r = 0; r < n; ++r) w[r] -= h * col[r];
+          }
+        }
       }
       double nrm = norm2(w, n);
       double inv = 1.0 / nrm;

@@ -91,6 +91,7 @@ class qgd_stats_t(C.Structure):
         ("last_backward_ms", C.c_double),
         ("last_total_ms", C.c_double),
         ("fast_path_launches", C.c_int64),
+        ("collectives", C.c_int64),
     ]
 
 

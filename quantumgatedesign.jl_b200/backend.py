@@ -26,7 +26,15 @@ EXPORTS = [
     "qgd_discrete_adjoint_device", "qgd_adjoint_phase1", "qgd_adjoint_phase2", "qgd_infidelity_real",
     "qgd_eval_controls", "qgd_compute_derivatives", "qgd_get_stats", "qgd_measure_fp64_peak",
     "qgd_eval_forward_forced", "qgd_eval_grad_forced", "qgd_eval_forward_tables", "qgd_discrete_adjoint_tables",
+    "qgd_set_option", "qgd_get_option", "qgd_synchronize", "qgd_comm_set_nccl_library", "qgd_comm_get_unique_id",
+    "qgd_comm_init_rank", "qgd_comm_finalize", "qgd_init_multi_gpu", "qgd_multi_n_gpus", "qgd_multi_handle",
+    "qgd_multi_set_nsteps", "qgd_multi_set_gmres_tolerances", "qgd_multi_discrete_adjoint", "qgd_multi_destroy",
 ]
+
+# option keys of qgd_set_option (include/qgd_b200.h)
+OPT_STRICT_MGS, OPT_DISABLE_FAST, OPT_DISABLE_DENSE_SWEEP, OPT_DISABLE_DENSE_DMMA, OPT_DENSE_TERMINAL = 1, 2, 3, 4, 5
+OPT_DISABLE_TMEM, OPT_SEG_STEPS, OPT_L2_PERSIST, OPT_LATENCY_WARPS, OPT_TERMINAL_EXCHANGE = 6, 7, 8, 9, 10
+SHARD_COLUMNS, SHARD_CONTROL_VECTORS = 0, 1
 
 
 class QGDError(RuntimeError):
@@ -82,6 +90,21 @@ def lib():
                                               c_double_p, c_int64_p]
         L.qgd_discrete_adjoint_tables.argtypes = [C.c_void_p, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
                                                   c_double_p, c_double_p, c_double_p]
+        L.qgd_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
+        L.qgd_get_option.argtypes = [C.c_void_p, C.c_int32, c_int64_p]
+        L.qgd_synchronize.argtypes = [C.c_void_p, C.c_void_p]
+        L.qgd_comm_set_nccl_library.argtypes = [C.c_char_p]
+        L.qgd_comm_get_unique_id.argtypes = [C.c_char_p]
+        L.qgd_comm_init_rank.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p]
+        L.qgd_comm_finalize.argtypes = [C.c_void_p]
+        L.qgd_init_multi_gpu.argtypes = [C.POINTER(_abi.qgd_problem_t), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]
+        L.qgd_multi_n_gpus.argtypes = [C.c_void_p]
+        L.qgd_multi_handle.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.qgd_multi_set_nsteps.argtypes = [C.c_void_p, C.c_int64]
+        L.qgd_multi_set_gmres_tolerances.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.qgd_multi_discrete_adjoint.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, C.c_int32, C.c_int32,
+                                                 c_double_p, c_double_p, c_double_p]
+        L.qgd_multi_destroy.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -119,7 +142,6 @@ class Handle:
         self.nsteps = prob.nsteps
         self.P = self._pack.n_coeff
         self.Nc = prob.N_operators
-        self.key = problem_key(prob, controls)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -139,6 +161,31 @@ class Handle:
 
     def set_gmres_tolerances(self, abstol, reltol):
         _check(lib().qgd_set_gmres_tolerances(self._h, float(abstol), float(reltol)))
+
+    def set_option(self, key, value):
+        """qgd_set_option: behaviour switches (OPT_* above), e.g. h.set_option(OPT_STRICT_MGS, 1)."""
+        _check(lib().qgd_set_option(self._h, int(key), int(value)))
+
+    def get_option(self, key):
+        out = np.zeros(1, dtype=np.int64)
+        _check(lib().qgd_get_option(self._h, int(key), _ip(out)))
+        return int(out[0])
+
+    def synchronize(self, stream_ptr=None):
+        """Complete (and check) an asynchronous discrete_adjoint_device call."""
+        _check(lib().qgd_synchronize(self._h, C.c_void_p(stream_ptr or 0)))
+
+    # -- multi-GPU, one process per GPU (NCCL inside the library)
+    def comm_init_rank(self, n_ranks, rank, unique_id: bytes):
+        """Attach an NCCL communicator (collective over the ranks) and take this rank's column block."""
+        assert len(unique_id) == 128
+        _check(lib().qgd_comm_init_rank(self._h, int(n_ranks), int(rank), unique_id))
+        c0, c1 = rank * self.nic // n_ranks, (rank + 1) * self.nic // n_ranks
+        self.col0, self.ncol = c0, c1 - c0
+
+    def comm_finalize(self):
+        _check(lib().qgd_comm_finalize(self._h))
+        self.col0, self.ncol = 0, self.nic
 
     def set_column_shard(self, col_begin, col_count):
         _check(lib().qgd_set_column_shard(self._h, int(col_begin), int(col_count)))
@@ -291,25 +338,123 @@ class Handle:
         return {f: getattr(s, f) for f, _ in _abi.qgd_stats_t._fields_}
 
 
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0 calls it and distributes the 128 bytes)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().qgd_comm_get_unique_id(buf))
+    return buf.raw
+
+
+class MultiGPU:
+    """qgd_init_multi_gpu: ONE process driving n GPUs (per-device handles + an NCCL communicator inside the library)."""
+
+    def __init__(self, prob, controls, n_gpus, devices=None):
+        self._pack = _abi.ProblemPack(prob, controls)
+        self._mg = C.c_void_p()
+        dev = (C.c_int32 * n_gpus)(*devices) if devices is not None else None
+        _check(lib().qgd_init_multi_gpu(self._pack.ref(), int(n_gpus), dev, C.byref(self._mg)))
+        self.n_gpus = int(n_gpus)
+        self.P = self._pack.n_coeff
+        self.N2 = prob.real_system_size
+        self.nic = prob.N_initial_conditions
+
+    def set_option(self, key, value):
+        for i in range(self.n_gpus):
+            h = C.c_void_p()
+            _check(lib().qgd_multi_handle(self._mg, i, C.byref(h)))
+            _check(lib().qgd_set_option(h, int(key), int(value)))
+
+    def set_nsteps(self, nsteps):
+        _check(lib().qgd_multi_set_nsteps(self._mg, int(nsteps)))
+
+    def set_gmres_tolerances(self, abstol, reltol):
+        _check(lib().qgd_multi_set_gmres_tolerances(self._mg, float(abstol), float(reltol)))
+
+    def discrete_adjoint(self, pcof, target_real, order=2, shard=SHARD_COLUMNS):
+        pc = Handle._pcof(pcof, self.P)
+        B = pc.shape[1]
+        tgt = np.asfortranarray(target_real, dtype=np.float64)
+        if tgt.shape != (self.N2, self.nic):
+            raise ValueError(f"target must be the real-stacked [2N, nic] = {(self.N2, self.nic)} array, got {tgt.shape}")
+        grad = np.zeros((self.P, B), order="F")
+        infid = np.zeros(B)
+        guard = np.zeros(B)
+        _check(lib().qgd_multi_discrete_adjoint(self._mg, _dp(pc), B, _dp(tgt), int(order), int(shard), _dp(grad), _dp(infid),
+                                                _dp(guard)))
+        return dict(grad=grad, infidelity=infid, guard_penalty=guard)
+
+    def close(self):
+        if getattr(self, "_mg", None) is not None and self._mg.value:
+            lib().qgd_multi_destroy(self._mg)
+            self._mg = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def problem_key(prob, controls):
-    """Identity of the immutable parts of (prob, controls); nsteps / tolerances are mutable knobs."""
+    """Fingerprint of the immutable parts of (prob, controls): shapes, physics parameters and a content hash of the
+    operators / initial conditions / control descriptors.  nsteps and the GMRES tolerances are mutable knobs
+    (examples/cnot3_optimize_gate.jl:51-55) and are re-synced on every call instead."""
+    import hashlib
+
+    import scipy.sparse as sp
+
     from .controls import as_control_list
 
-    return (id(prob), tuple(id(c) for c in as_control_list(controls)), prob.preconditioner_type, prob.tf)
+    hsh = hashlib.blake2b(digest_size=16)
+
+    def feed(a):
+        if sp.issparse(a):
+            a = a.tocsc()
+            for part in (a.indptr, a.indices, a.data):
+                hsh.update(np.ascontiguousarray(part).tobytes())
+        else:
+            hsh.update(np.ascontiguousarray(np.asarray(a, dtype=np.float64)).tobytes())
+
+    for a in (prob.system_sym, prob.system_asym, *prob.sym_operators, *prob.asym_operators, prob.u0, prob.v0,
+              prob.guard_subspace_projector):
+        feed(a)
+    ctl = tuple(_control_descriptor(c) for c in as_control_list(controls))
+    return (prob.N_tot_levels, prob.N_ess_levels, prob.N_initial_conditions, prob.N_operators, float(prob.tf),
+            int(prob.preconditioner_type), ctl, hsh.hexdigest())
 
 
-_HANDLES = {}
+def _control_descriptor(c):
+    """Everything qgd_create reads from a control (type and shape parameters; coefficient values are not part of it)."""
+    fields = []
+    for name in ("N_coeff", "tf", "N_amplitudes", "D1", "degree", "N_basis_functions"):
+        if hasattr(c, name):
+            fields.append((name, float(getattr(c, name))))
+    base = getattr(c, "base_control", None)
+    if base is not None:
+        fields.append(("carrier", _control_descriptor(base), tuple(float(x) for x in c.carrier_frequencies)))
+    return (type(c).__name__, tuple(fields))
+
+
+# Device handles of the api functions, keyed on the CONTENT fingerprint above (never on id(): CPython reuses the ids
+# of freed objects, and a temporary problem must not inherit the operators of a dead one).  Least recently used
+# handles are closed beyond `HANDLE_CACHE_SIZE`, which also bounds the device memory the cache can pin.
+HANDLE_CACHE_SIZE = 4
+_HANDLES = {}  # key -> Handle, insertion order = recency
 
 
 def get_handle(prob, controls, device: int = -1) -> Handle:
     """Cached device handle for (prob, controls); follows the reference's in-place mutation of
     prob.nsteps / prob.gmres_abstol / prob.gmres_reltol (examples/cnot3_optimize_gate.jl:51-55)."""
     key = (problem_key(prob, controls), device)
-    h = _HANDLES.get(key)
+    h = _HANDLES.pop(key, None)
     if h is None:
         h = Handle(prob, controls, device)
         h._tol = (prob.gmres_abstol, prob.gmres_reltol)
-        _HANDLES[key] = h
+    _HANDLES[key] = h  # most recently used last
+    while len(_HANDLES) > HANDLE_CACHE_SIZE:
+        _, old = next(iter(_HANDLES.items()))
+        _HANDLES.pop(next(iter(_HANDLES)))
+        old.close()
     if h.nsteps != prob.nsteps:
         h.set_nsteps(prob.nsteps)
     if h._tol != (prob.gmres_abstol, prob.gmres_reltol):

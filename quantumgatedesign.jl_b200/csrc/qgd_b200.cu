@@ -87,6 +87,25 @@ __global__ void k_finalize(int P, int ncol, int B, const double* gradcol, const 
   }
 }
 
+// Column sharding with the scalar exchange: this rank's part of dot(final_state, R), dot(final_state, T)
+// (src/eval_grad_discrete_adjoint.jl:27-28), one warp per control vector; final_all holds the owned columns in place.
+__global__ void k_partial_dots(int N, int nic, int col0, int ncol, int B, const double* final_all, const double* target, double* dots) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  if (b >= B) return;
+  const int N2 = 2 * N;
+  double dR = 0.0, dT = 0.0;
+  for (int col = col0; col < col0 + ncol; ++col) {
+    const double* p = final_all + (size_t)N2 * ((size_t)col + (size_t)nic * b);
+    const double* R = target + (size_t)N2 * col;
+    for (int r = lane; r < N; r += 32) {
+      dR += p[r] * R[r] + p[N + r] * R[N + r];
+      dT += p[r] * R[N + r] - p[N + r] * R[r];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { dR += __shfl_xor_sync(0xffffffffu, dR, o); dT += __shfl_xor_sync(0xffffffffu, dT, o); }
+  if (lane == 0) { dots[2 * b] = dR; dots[2 * b + 1] = dT; }
+}
+
 // FP64 FMA throughput micro-benchmark (roofline denominator MEASURED_PEAKS.json does not carry).
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3, a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
@@ -260,7 +279,7 @@ void validate_and_load(qgd_handle* h, const qgd_problem_t* p) {
   // ---- does the problem have the structure of the register-operator fast path?  diagonal drift, <= 2 entries per
   // row and control operator, diagonal guard projector, N <= 64 (qgd_fast.cuh)
   {
-    bool ok = n <= 64 && h->Nc >= 1 && L.L[0] <= 1 && LW <= 1 && getenv("QGD_DISABLE_FAST") == nullptr;
+    bool ok = n <= 64 && h->Nc >= 1 && L.L[0] <= 1 && LW <= 1;
     for (int k = 1; k < L.n_ops && ok; ++k) ok = L.L[k] <= 2;
     if (ok && L.L[0] == 1) {
       const int* col = reinterpret_cast<const int*>(h->blob.data() + L.off_col[0]);
@@ -470,9 +489,30 @@ void iters_out(qgd_handle* h, int64_t* dst, DevBuf& src, size_t n) {  // device 
 
 void reset_stats(qgd_handle* h) { h->stats = qgd_stats_t{}; }
 
+// The sweeps raise a sticky device error word instead of returning wrong numbers silently (wait_segment in
+// qgd_fast.cuh).  Called by every synchronising entry point after its stream synchronisation.
+void check_device_error(qgd_handle* h) {
+  if (!h->d_counter.cap) return;
+  int err = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&err, h->d_counter.as<int>() + 1, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (err != 0) {
+    CUDA_CHECK(cudaMemsetAsync(h->d_counter.as<int>() + 1, 0, 4, h->stream));
+    h->hist_valid = false;
+    throw QgdError(QGD_ESTATE, "a sweep kernel gave up waiting for a time segment that was never published (device error word " +
+                                   std::to_string(err) + "): the results of this call are not valid");
+  }
+}
+
+// the control vectors the resident history belongs to (history_precomputed is only honoured for the same ones)
+void remember_hist_pcof(qgd_handle* h, const double* pcof, int B) {
+  if (pcof) h->hist_pcof.assign(pcof, pcof + (size_t)h->P * B);
+  else h->hist_pcof.clear();
+}
+
 // ---- register-operator fast path dispatch (false: shape not built / not applicable -> generic kernels)
 bool fast_applicable(const qgd_handle* h, int m) {
-  return h->fast_ok && h->precond != QGD_PRECOND_LU && m >= 1 && m <= QGD_FAST_MAX_M;
+  return h->fast_ok && !h->opt[QGD_OPT_DISABLE_FAST] && h->precond != QGD_PRECOND_LU && m >= 1 && m <= QGD_FAST_MAX_M;
 }
 #define QGD_FAST_SWITCH(m, NAME, ...)                   \
   bool done_ = false;                                   \
@@ -487,13 +527,26 @@ bool fast_applicable(const qgd_handle* h, int m) {
   }                                                     \
   if (done_) h->stats.fast_path_launches++;             \
   return done_;
+bool try_forward_fast_default(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_forward_fast, h, d, a, h->fast_el, h->Nc)
+}
+bool try_forward_fast_strict(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_forward_fast_strict, h, d, a, h->fast_el, h->Nc)
+}
+bool try_backward_fast_default(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_backward_fast, h, d, a, h->fast_el, h->Nc)
+}
+bool try_backward_fast_strict(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_backward_fast_strict, h, d, a, h->fast_el, h->Nc)
+}
+// QGD_OPT_STRICT_MGS selects the strict modified Gram-Schmidt instantiation of the same sweeps
 bool try_forward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (!fast_applicable(h, d.m)) return false;
-  QGD_FAST_SWITCH(d.m, launch_forward_fast, h, d, a, h->fast_el, h->Nc)
+  return h->opt[QGD_OPT_STRICT_MGS] ? try_forward_fast_strict(h, d, a) : try_forward_fast_default(h, d, a);
 }
 bool try_backward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (!fast_applicable(h, d.m)) return false;
-  QGD_FAST_SWITCH(d.m, launch_backward_fast, h, d, a, h->fast_el, h->Nc)
+  return h->opt[QGD_OPT_STRICT_MGS] ? try_backward_fast_strict(h, d, a) : try_backward_fast_default(h, d, a);
 }
 bool try_derivs_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a, double* uv, int ncols, const double* cv, int adjoint) {
   if (!fast_applicable(h, d.m)) return false;
@@ -591,7 +644,9 @@ void run_adjoint(qgd_handle* h, int B, int order, const double* d_target, bool w
     CUDA_CHECK(cudaMemsetAsync(h->d_iters_a.p, 0, (size_t)h->nsteps * h->ncol * B * 4, h->stream));
     a.iters_term = h->d_iters_t.as<int>();
   }
-  if (!try_terminal_dense(h, d, a)) { QGD_DISPATCH_EL(el, launch_terminal, h, d, a); }
+  const bool scalar_exchange = h->comm && h->opt[QGD_OPT_TERMINAL_EXCHANGE] == 1;
+  if (scalar_exchange) { a.dots_in = h->d_dots.as<double>(); a.term_col0 = h->col0; a.term_ncol = h->ncol; }
+  if (scalar_exchange || !try_terminal_dense(h, d, a)) { QGD_DISPATCH_EL(el, launch_terminal, h, d, a); }
   a.iters = want_iters ? h->d_iters_a.as<int>() : nullptr;
   if (want_lambda0) {
     const size_t sz = (size_t)h->N2 * (h->nsteps + 1) * h->ncol * B * 8;
@@ -675,7 +730,8 @@ int qgd_destroy(qgd_handle_t* h) {
                     &h->d_cvals, &h->d_history, &h->d_final, &h->d_final_all, &h->d_terminal, &h->d_lambda0, &h->d_lamhist,
                     &h->d_gradcol, &h->d_grad, &h->d_guardcol, &h->d_guard, &h->d_infid, &h->d_iters_f, &h->d_iters_a,
                     &h->d_iters_t, &h->d_target, &h->d_forcing, &h->d_V, &h->d_H, &h->d_scratch, &h->d_counter, &h->d_progress, &h->d_carry,
-                    &h->d_theta_op, &h->d_dense, &h->d_comb, &h->d_dense_ws};
+                    &h->d_theta_op, &h->d_dense, &h->d_comb, &h->d_dense_ws, &h->d_pack, &h->d_dots};
+  if (h->comm) { cudaStreamSynchronize(h->stream); qgd_nccl::destroy(h->comm); h->comm = nullptr; }
   for (DevBuf* b : bufs) b->release();
   if (h->l2_carved) cudaCtxResetPersistingL2Cache();  // hand the persisting L2 lines of the workspace window back
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -684,11 +740,43 @@ int qgd_destroy(qgd_handle_t* h) {
   return QGD_OK;
 }
 
+// Setting a knob to the value it already has is a no-op: a binding may re-sync the three mutable fields of the
+// reference's SchrodingerProb before every call without invalidating the resident history.
 int qgd_set_nsteps(qgd_handle_t* h, int64_t nsteps) {
-  return guarded([&]() { require(h && nsteps >= 1, "nsteps must be >= 1"); h->nsteps = nsteps; h->hist_valid = false; });
+  return guarded([&]() {
+    require(h && nsteps >= 1, "nsteps must be >= 1");
+    if (h->nsteps == nsteps) return;
+    h->nsteps = nsteps; h->hist_valid = false;
+  });
 }
 int qgd_set_gmres_tolerances(qgd_handle_t* h, double abstol, double reltol) {
-  return guarded([&]() { require(h != nullptr, "null handle"); h->abstol = abstol; h->reltol = reltol; h->hist_valid = false; });
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    if (h->abstol == abstol && h->reltol == reltol) return;
+    h->abstol = abstol; h->reltol = reltol; h->hist_valid = false;
+  });
+}
+int qgd_set_option(qgd_handle_t* h, int32_t key, int64_t value) {
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    switch (key) {
+      case QGD_OPT_STRICT_MGS: case QGD_OPT_DISABLE_FAST: case QGD_OPT_DISABLE_DENSE_SWEEP: case QGD_OPT_DISABLE_DENSE_DMMA:
+      case QGD_OPT_DISABLE_TMEM: case QGD_OPT_L2_PERSIST:
+        require(value == 0 || value == 1, "option value must be 0 or 1"); break;
+      case QGD_OPT_DENSE_TERMINAL: require(value >= 0 && value <= 2, "QGD_OPT_DENSE_TERMINAL must be 0, 1 or 2"); break;
+      case QGD_OPT_SEG_STEPS: require(value >= 0 && value <= (1 << 30), "QGD_OPT_SEG_STEPS must be >= 0"); break;
+      case QGD_OPT_LATENCY_WARPS: require(value >= 0 && value <= QGD_WARPS_PER_CTA, "QGD_OPT_LATENCY_WARPS must be 0..8"); break;
+      case QGD_OPT_TERMINAL_EXCHANGE: require(value == 0 || value == 1, "QGD_OPT_TERMINAL_EXCHANGE must be 0 or 1"); break;
+      default: throw QgdError(QGD_EINVAL, "unknown option key " + std::to_string(key));
+    }
+    if (h->opt[key] != value) { h->opt[key] = value; h->hist_valid = false; }
+  });
+}
+int qgd_get_option(qgd_handle_t* h, int32_t key, int64_t* value) {
+  return guarded([&]() {
+    require(h && value && key >= 1 && key <= QGD_OPT_MAX, "bad arguments");
+    *value = h->opt[key];
+  });
 }
 int qgd_set_column_shard(qgd_handle_t* h, int64_t col_begin, int64_t col_count) {
   return guarded([&]() {
@@ -707,10 +795,12 @@ int qgd_eval_forward(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32
     h->d_pcof.reserve((size_t)std::max(h->P, 1) * B * 8);
     h2d(h, h->d_pcof.p, pcof, (size_t)h->P * B * 8);
     run_forward(h, h->d_pcof.as<double>(), B, order, save_every, gmres_iters != nullptr);
+    remember_hist_pcof(h, pcof, B);
     const int nslots = 1 + (int)(h->nsteps / save_every);
     if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * nslots * h->ncol * B * 8);
     if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
     finish_timing(h, true, false);
   });
@@ -734,6 +824,7 @@ int qgd_eval_forward_forced(qgd_handle_t* h, const double* pcof, int64_t n_batch
     if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * nslots * h->ncol * B * 8);
     if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
     finish_timing(h, true, false);
   });
@@ -756,6 +847,7 @@ int qgd_eval_grad_forced(qgd_handle_t* h, const double* pcof, const double* targ
     d2h(h, dfs.data(), h->d_scratch.p, dfs.size() * 8);
     d2h(h, gc.data(), h->d_guardcol.p, gc.size() * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     // d infidelity / d theta = -(2 / N_ess^2) (<psi,R><dpsi,R> + <psi,T><dpsi,T>), T = [R_im; -R_re]  (:134-147)
     auto dots = [&](const double* psi, double& dR, double& dT) {
       dR = 0.0; dT = 0.0;
@@ -814,6 +906,7 @@ int qgd_eval_forward_tables(qgd_handle_t* h, int64_t n_batch, int32_t order, int
     if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * nslots * h->ncol * B * 8);
     if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
     finish_timing(h, true, false);
   });
@@ -843,6 +936,7 @@ int qgd_discrete_adjoint_tables(qgd_handle_t* h, int64_t n_batch, int32_t order,
     if (infidelity) d2h(h, infidelity, h->d_infid.p, (size_t)B * 8);
     if (guard_penalty) d2h(h, guard_penalty, h->d_guard.p, (size_t)B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     finish_timing(h, true, true);
   });
 }
@@ -869,6 +963,7 @@ int qgd_adjoint_phase1(qgd_handle_t* h, const double* pcof, int64_t n_batch, int
     if (final_state_local) d2h(h, final_state_local, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
     if (guard_local) d2h(h, guard_local, h->d_guard.p, (size_t)B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     h->phase_B = B; h->phase_order = order;
     finish_timing(h, true, false);
   });
@@ -890,16 +985,92 @@ int qgd_adjoint_phase2(qgd_handle_t* h, const double* target, const double* fina
     if (grad_local) d2h(h, grad_local, h->d_grad.p, (size_t)h->P * B * 8);
     if (infidelity) d2h(h, infidelity, h->d_infid.p, (size_t)B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     finish_timing(h, false, true);
   });
 }
+
+// ---- one gradient evaluation in stages, so that several handles (column shards of ONE evaluation on several GPUs)
+// can be driven in lock step with the two NCCL exchanges grouped between the stages ---------------------------------
+namespace {
+struct AdjCall {
+  const double* d_pcof; int B; int order; const double* d_target;
+  bool precomputed, want_iters, want_lambda0, want_forcing;
+  double *grad_out, *infid_out, *guard_out;  // device; with a communicator: the packed buffer, copied out after the all-reduce
+};
+
+// forward sweep (unless the history is resident), guard partials, own final states placed into the all-columns array
+void adj_stage1(qgd_handle* h, const AdjCall& c) {
+  const int B = c.B, m = c.order / 2;
+  if (c.precomputed) {
+    build_preconditioner(h, c.order);
+    ensure_table(h, m);
+    compute_cvals(h, m, B, c.d_pcof);
+    CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
+    CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+  } else {
+    run_forward(h, c.d_pcof, B, c.order, 1, c.want_iters);
+  }
+  run_guard(h, B, c.order, c.want_forcing);
+  const size_t all_bytes = (size_t)h->N2 * h->nic * B * 8;
+  h->d_final_all.reserve(all_bytes);
+  if (!h->comm) {  // all columns are local: the final states are the terminal kernel's input as they are
+    CUDA_CHECK(cudaMemcpyAsync(h->d_final_all.p, h->d_final.p, all_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return;
+  }
+  // column shard: [2N][ncol][B] -> the owned columns of [2N][nic][B], zero elsewhere (x + 0 = x: the all-reduce that
+  // follows IS the all-gather, for uneven shards too, and is bitwise deterministic)
+  CUDA_CHECK(cudaMemsetAsync(h->d_final_all.p, 0, all_bytes, h->stream));
+  CUDA_CHECK(cudaMemcpy2DAsync(h->d_final_all.as<double>() + (size_t)h->N2 * h->col0, (size_t)h->N2 * h->nic * 8, h->d_final.p,
+                               (size_t)h->N2 * h->ncol * 8, (size_t)h->N2 * h->ncol * 8, (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->opt[QGD_OPT_TERMINAL_EXCHANGE] == 1) {
+    h->d_dots.reserve((size_t)2 * B * 8);
+    k_partial_dots<<<B, 32, 0, h->stream>>>(h->N, h->nic, h->col0, h->ncol, B, h->d_final_all.as<double>(), c.d_target, h->d_dots.as<double>());
+    CUDA_CHECK(cudaGetLastError());
+    h->stats.kernel_launches++;
+  }
+}
+// exchange 1 (between the sweeps): the final states of all columns -- or only the two inner products per control vector
+void adj_exchange1(qgd_handle* h, const AdjCall& c) {
+  if (!h->comm) return;
+  if (h->opt[QGD_OPT_TERMINAL_EXCHANGE] == 1) qgd_nccl::allreduce_sum(h->comm, h->d_dots.as<double>(), (size_t)2 * c.B, h->stream);
+  else qgd_nccl::allreduce_sum(h->comm, h->d_final_all.as<double>(), (size_t)h->N2 * h->nic * c.B, h->stream);
+  h->stats.collectives++;
+}
+void adj_stage2(qgd_handle* h, const AdjCall& c) {
+  double *g = c.grad_out, *gu = c.guard_out;
+  if (h->comm) {  // [grad P*B | guard B] contiguous: ONE all-reduce at the end of the evaluation
+    h->d_pack.reserve(((size_t)std::max(h->P, 1) * c.B + c.B) * 8);
+    g = h->d_pack.as<double>(); gu = g + (size_t)h->P * c.B;
+  }
+  run_adjoint(h, c.B, c.order, c.d_target, c.want_iters, c.want_lambda0, g, c.infid_out, gu);
+}
+void adj_exchange2(qgd_handle* h, const AdjCall& c) {
+  if (!h->comm) return;
+  qgd_nccl::allreduce_sum(h->comm, h->d_pack.as<double>(), (size_t)h->P * c.B + c.B, h->stream);
+  h->stats.collectives++;
+}
+void adj_stage3(qgd_handle* h, const AdjCall& c) {
+  if (!h->comm) return;
+  const double* g = h->d_pack.as<double>();
+  if (c.grad_out && h->P > 0) CUDA_CHECK(cudaMemcpyAsync(c.grad_out, g, (size_t)h->P * c.B * 8, cudaMemcpyDeviceToDevice, h->stream));
+  if (c.guard_out) CUDA_CHECK(cudaMemcpyAsync(c.guard_out, g + (size_t)h->P * c.B, (size_t)c.B * 8, cudaMemcpyDeviceToDevice, h->stream));
+}
+void adj_all_stages(qgd_handle* h, const AdjCall& c) {
+  adj_stage1(h, c); adj_exchange1(h, c); adj_stage2(h, c); adj_exchange2(h, c); adj_stage3(h, c);
+}
+void require_all_columns_or_comm(const qgd_handle* h) {
+  if (h->ncol != h->nic && !h->comm)
+    throw QgdError(QGD_ESTATE, "column-sharded handle without a communicator: attach one (qgd_comm_init_rank) or use qgd_adjoint_phase1/phase2");
+}
+}  // namespace
 
 int qgd_discrete_adjoint(qgd_handle_t* h, const double* pcof, int64_t n_batch, const double* target, int32_t order,
                          int32_t history_precomputed, double* grad, double* infidelity, double* guard_penalty, double* history,
                          double* lambda_history, double* adjoint_forcing, int64_t* iters_fwd, int64_t* iters_adj, int64_t* iters_term) {
   return guarded([&]() {
     require(h && pcof && target && n_batch >= 1, "bad arguments");
-    if (h->ncol != h->nic) throw QgdError(QGD_ESTATE, "column-sharded handle: use qgd_adjoint_phase1/phase2");
+    require_all_columns_or_comm(h);
     CUDA_CHECK(cudaSetDevice(h->device));
     reset_stats(h);
     check_order(order);
@@ -914,22 +1085,17 @@ int qgd_discrete_adjoint(qgd_handle_t* h, const double* pcof, int64_t n_batch, c
       if (!(h->hist_valid && h->hist_B == B && h->hist_order == order && h->hist_nsteps == h->nsteps && h->hist_save == 1))
         throw QgdError(QGD_ESTATE, "history_precomputed: no matching history is resident on the device (call qgd_eval_forward with "
                                    "saveEveryNsteps=1, the same batch and order first)");
-      build_preconditioner(h, order);
-      ensure_table(h, m);
-      compute_cvals(h, m, B, h->d_pcof.as<double>());
-      CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
-      CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
-    } else {
-      run_forward(h, h->d_pcof.as<double>(), B, order, 1, want_iters);
+      // The reference combines whatever history array the caller passes with the new pcof (eval_grad_discrete_adjoint.jl:
+      // 118-140); here the history stays on the device, so it must be the one of these very control vectors.
+      if (h->hist_pcof.size() != (size_t)h->P * B || !std::equal(h->hist_pcof.begin(), h->hist_pcof.end(), pcof))
+        throw QgdError(QGD_ESTATE, "history_precomputed: the resident history was computed for different control vectors");
     }
-    run_guard(h, B, order, adjoint_forcing != nullptr);
-    // all columns are local: the final states are the terminal kernel's input as they are
-    h->d_final_all.reserve((size_t)h->N2 * h->nic * B * 8);
-    CUDA_CHECK(cudaMemcpyAsync(h->d_final_all.p, h->d_final.p, (size_t)h->N2 * h->nic * B * 8, cudaMemcpyDeviceToDevice, h->stream));
     h->d_infid.reserve((size_t)B * 8); h->d_guard.reserve((size_t)B * 8);
     h->d_grad.reserve((size_t)std::max(h->P, 1) * B * 8);
-    run_adjoint(h, B, order, h->d_target.as<double>(), want_iters, lambda_history != nullptr, h->d_grad.as<double>(),
-                h->d_infid.as<double>(), h->d_guard.as<double>());
+    AdjCall c{h->d_pcof.as<double>(), B, order, h->d_target.as<double>(), history_precomputed != 0, want_iters, lambda_history != nullptr,
+              adjoint_forcing != nullptr, h->d_grad.as<double>(), h->d_infid.as<double>(), h->d_guard.as<double>()};
+    adj_all_stages(h, c);
+    if (!history_precomputed) remember_hist_pcof(h, pcof, B);
     if (lambda_history) {
       const int el = pick_el(h->N);
       const size_t sz = (size_t)h->N2 * (m + 1) * Nt * h->ncol * B * 8;
@@ -946,6 +1112,7 @@ int qgd_discrete_adjoint(qgd_handle_t* h, const double* pcof, int64_t n_batch, c
     if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * Nt * h->ncol * B * 8);
     if (adjoint_forcing) d2h(h, adjoint_forcing, h->d_forcing.p, (size_t)h->N2 * Nt * h->ncol * B * 8);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
     if (!history_precomputed) iters_out(h, iters_fwd, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
     iters_out(h, iters_adj, h->d_iters_a, (size_t)h->nsteps * h->ncol * B);
     iters_out(h, iters_term, h->d_iters_t, (size_t)h->nic * B);
@@ -957,30 +1124,205 @@ int qgd_discrete_adjoint_device(qgd_handle_t* h, const double* d_pcof, int64_t n
                                 double* d_grad, double* d_infidelity, double* d_guard_penalty, void* stream) {
   return guarded([&]() {
     require(h && d_pcof && d_target && d_grad && d_infidelity && d_guard_penalty && n_batch >= 1, "bad arguments");
-    if (h->ncol != h->nic) throw QgdError(QGD_ESTATE, "column-sharded handle: use qgd_adjoint_phase1/phase2");
+    require_all_columns_or_comm(h);
     CUDA_CHECK(cudaSetDevice(h->device));
     reset_stats(h);
+    check_order(order);
     cudaStream_t own = h->stream;
     if (stream) h->stream = reinterpret_cast<cudaStream_t>(stream);
     try {
-      const int B = (int)n_batch;
-      run_forward(h, d_pcof, B, order, 1, false);
-      run_guard(h, B, order, false);
-      h->d_final_all.reserve((size_t)h->N2 * h->nic * B * 8);
-      CUDA_CHECK(cudaMemcpyAsync(h->d_final_all.p, h->d_final.p, (size_t)h->N2 * h->nic * B * 8, cudaMemcpyDeviceToDevice, h->stream));
-      run_adjoint(h, B, order, d_target, false, false, d_grad, d_infidelity, d_guard_penalty);
+      AdjCall c{d_pcof, (int)n_batch, order, d_target, false, false, false, false, d_grad, d_infidelity, d_guard_penalty};
+      adj_all_stages(h, c);
+      remember_hist_pcof(h, nullptr, (int)n_batch);  // the control vectors never passed through the host: not reusable by history_precomputed
     } catch (...) { h->stream = own; throw; }
     h->stream = own;
+  });
+}
+
+// Synchronise the handle's stream (or `stream`) and report the sticky device error word of the sweeps: the way to check an
+// asynchronous qgd_discrete_adjoint_device call.
+int qgd_synchronize(qgd_handle_t* h, void* stream) {
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    if (stream) CUDA_CHECK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
+  });
+}
+
+// ---- multi-GPU, one process per GPU: attach an NCCL communicator to the handle and shard the columns ----------------
+int qgd_comm_set_nccl_library(const char* path) {
+  return guarded([&]() { qgd_nccl::set_library(path); });
+}
+int qgd_comm_get_unique_id(unsigned char* id128) {
+  return guarded([&]() { require(id128 != nullptr, "bad arguments"); qgd_nccl::unique_id(id128); });
+}
+int qgd_comm_init_rank(qgd_handle_t* h, int32_t n_ranks, int32_t rank, const unsigned char* id128) {
+  return guarded([&]() {
+    require(h && id128 && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad arguments");
+    if (n_ranks > h->nic) throw QgdError(QGD_EINVAL, "more ranks than initial-condition columns: shard control vectors over the extra GPUs instead");
+    if (h->comm) throw QgdError(QGD_ESTATE, "the handle already has a communicator");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->comm = qgd_nccl::init_rank(n_ranks, rank, id128);
+    h->comm_rank = rank; h->comm_size = n_ranks;
+    const int c0 = (int)((int64_t)rank * h->nic / n_ranks), c1 = (int)((int64_t)(rank + 1) * h->nic / n_ranks);
+    h->col0 = c0; h->ncol = c1 - c0; h->hist_valid = false;
+  });
+}
+int qgd_comm_finalize(qgd_handle_t* h) {
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    if (!h->comm) return;
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    qgd_nccl::destroy(h->comm);
+    h->comm = nullptr; h->comm_rank = 0; h->comm_size = 1;
+    h->col0 = 0; h->ncol = h->nic; h->hist_valid = false;
+  });
+}
+
+// ---- multi-GPU, one process driving n GPUs -------------------------------------------------------------------------------
+struct qgd_multi {
+  std::vector<qgd_handle*> hs;
+  std::vector<int> devices;
+};
+
+int qgd_init_multi_gpu(const qgd_problem_t* prob, int32_t n_gpus, const int32_t* devices, qgd_multi_t** out) {
+  qgd_multi* mg = nullptr;
+  int rc = guarded([&]() {
+    require(prob && out && n_gpus >= 1, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw QgdError(QGD_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (n_gpus > ndev) throw QgdError(QGD_EINVAL, "qgd_init_multi_gpu: " + std::to_string(n_gpus) + " GPUs requested, " + std::to_string(ndev) + " visible");
+    mg = new qgd_multi();
+    for (int i = 0; i < n_gpus; ++i) mg->devices.push_back(devices ? devices[i] : i);
+    for (int i = 0; i < n_gpus; ++i) {
+      qgd_handle_t* h = nullptr;
+      const int rc1 = qgd_create(prob, mg->devices[i], &h);
+      if (rc1 != QGD_OK) throw QgdError(rc1, g_err);
+      mg->hs.push_back(h);
+    }
+    if (n_gpus > 1) {
+      std::vector<void*> comms((size_t)n_gpus, nullptr);
+      qgd_nccl::init_all(comms.data(), n_gpus, mg->devices.data());
+      for (int i = 0; i < n_gpus; ++i) { mg->hs[i]->comm = comms[i]; mg->hs[i]->comm_rank = i; mg->hs[i]->comm_size = n_gpus; }
+    }
+    *out = mg;
+  });
+  if (rc != QGD_OK && mg) { std::string keep = g_err; qgd_multi_destroy(mg); g_err = keep; }
+  return rc;
+}
+int qgd_multi_n_gpus(qgd_multi_t* mg) { return mg ? (int)mg->hs.size() : 0; }
+int qgd_multi_handle(qgd_multi_t* mg, int32_t i, qgd_handle_t** out) {
+  return guarded([&]() { require(mg && out && i >= 0 && i < (int)mg->hs.size(), "bad arguments"); *out = mg->hs[i]; });
+}
+int qgd_multi_set_nsteps(qgd_multi_t* mg, int64_t nsteps) {
+  if (!mg) return QGD_EINVAL;
+  for (qgd_handle* h : mg->hs) { const int rc = qgd_set_nsteps(h, nsteps); if (rc) return rc; }
+  return QGD_OK;
+}
+int qgd_multi_set_gmres_tolerances(qgd_multi_t* mg, double abstol, double reltol) {
+  if (!mg) return QGD_EINVAL;
+  for (qgd_handle* h : mg->hs) { const int rc = qgd_set_gmres_tolerances(h, abstol, reltol); if (rc) return rc; }
+  return QGD_OK;
+}
+int qgd_multi_destroy(qgd_multi_t* mg) {
+  if (!mg) return QGD_OK;
+  for (qgd_handle* h : mg->hs) qgd_destroy(h);
+  delete mg;
+  return QGD_OK;
+}
+
+int qgd_multi_discrete_adjoint(qgd_multi_t* mg, const double* pcof, int64_t n_batch, const double* target, int32_t order,
+                               int32_t shard, double* grad, double* infidelity, double* guard_penalty) {
+  return guarded([&]() {
+    require(mg && pcof && target && n_batch >= 1, "bad arguments");
+    require(shard == QGD_SHARD_COLUMNS || shard == QGD_SHARD_CONTROL_VECTORS, "shard must be QGD_SHARD_COLUMNS or QGD_SHARD_CONTROL_VECTORS");
+    check_order(order);
+    const int G = (int)mg->hs.size();
+    const int Btot = (int)n_batch;
+    std::vector<AdjCall> calls((size_t)G);
+    std::vector<int> b0((size_t)G, 0), nb((size_t)G, Btot);
+    std::vector<char> active((size_t)G, 1);
+    for (int i = 0; i < G; ++i) {
+      qgd_handle* h = mg->hs[i];
+      const int P = h->P;
+      if (shard == QGD_SHARD_COLUMNS) {
+        if (G > h->nic) throw QgdError(QGD_EINVAL, "more GPUs than initial-condition columns: use QGD_SHARD_CONTROL_VECTORS");
+        const int c0 = (int)((int64_t)i * h->nic / G), c1 = (int)((int64_t)(i + 1) * h->nic / G);
+        if (h->col0 != c0 || h->ncol != c1 - c0) { h->col0 = c0; h->ncol = c1 - c0; h->hist_valid = false; }
+      } else {
+        if (h->col0 != 0 || h->ncol != h->nic) { h->col0 = 0; h->ncol = h->nic; h->hist_valid = false; }
+        b0[i] = (int)((int64_t)i * Btot / G); nb[i] = (int)((int64_t)(i + 1) * Btot / G) - b0[i];
+        active[i] = nb[i] > 0;
+      }
+      if (!active[i]) continue;
+      CUDA_CHECK(cudaSetDevice(h->device));
+      reset_stats(h);
+      const int B = nb[i];
+      h->d_pcof.reserve((size_t)std::max(P, 1) * B * 8);
+      h2d(h, h->d_pcof.p, pcof + (size_t)P * b0[i], (size_t)P * B * 8);
+      h->d_target.reserve((size_t)h->N2 * h->nic * 8);
+      h2d(h, h->d_target.p, target, (size_t)h->N2 * h->nic * 8);
+      h->d_infid.reserve((size_t)B * 8); h->d_guard.reserve((size_t)B * 8);
+      h->d_grad.reserve((size_t)std::max(P, 1) * B * 8);
+      calls[i] = AdjCall{h->d_pcof.as<double>(), B, order, h->d_target.as<double>(), false, false, false, false,
+                         h->d_grad.as<double>(), h->d_infid.as<double>(), h->d_guard.as<double>()};
+    }
+    // control-vector sharding has no collective: detach the communicators for the duration of the call
+    std::vector<void*> comms((size_t)G, nullptr);
+    if (shard == QGD_SHARD_CONTROL_VECTORS) for (int i = 0; i < G; ++i) { comms[i] = mg->hs[i]->comm; mg->hs[i]->comm = nullptr; }
+    auto restore = [&]() { if (shard == QGD_SHARD_CONTROL_VECTORS) for (int i = 0; i < G; ++i) mg->hs[i]->comm = comms[i]; };
+    try {
+      const bool coll = shard == QGD_SHARD_COLUMNS && G > 1;
+      auto each = [&](void (*f)(qgd_handle*, const AdjCall&), bool grouped) {
+        if (grouped) qgd_nccl::group_start();
+        for (int i = 0; i < G; ++i) {
+          if (!active[i]) continue;
+          CUDA_CHECK(cudaSetDevice(mg->hs[i]->device));
+          f(mg->hs[i], calls[i]);
+        }
+        if (grouped) qgd_nccl::group_end();
+      };
+      each(adj_stage1, false);
+      each(adj_exchange1, coll);
+      each(adj_stage2, false);
+      each(adj_exchange2, coll);
+      each(adj_stage3, false);
+      for (int i = 0; i < G; ++i) {
+        if (!active[i]) continue;
+        qgd_handle* h = mg->hs[i];
+        CUDA_CHECK(cudaSetDevice(h->device));
+        const int B = nb[i];
+        const bool writer = shard == QGD_SHARD_CONTROL_VECTORS || i == 0;  // column sharding: every GPU holds the complete result
+        if (writer) {
+          if (grad) d2h(h, grad + (size_t)h->P * b0[i], h->d_grad.p, (size_t)h->P * B * 8);
+          if (infidelity) d2h(h, infidelity + b0[i], h->d_infid.p, (size_t)B * 8);
+          if (guard_penalty) d2h(h, guard_penalty + b0[i], h->d_guard.p, (size_t)B * 8);
+        }
+        remember_hist_pcof(h, pcof + (size_t)h->P * b0[i], B);
+      }
+      for (int i = 0; i < G; ++i) {
+        if (!active[i]) continue;
+        qgd_handle* h = mg->hs[i];
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        check_device_error(h);
+        finish_timing(h, true, true);
+      }
+    } catch (...) { restore(); throw; }
+    restore();
   });
 }
 
 int qgd_infidelity_real(qgd_handle_t* h, const double* final_state, const double* target, int64_t n_batch, double* infidelity) {
   return guarded([&]() {
     require(h && final_state && target && infidelity && n_batch >= 1, "bad arguments");
-    // tiny host-independent reduction done on the device for consistency with the gradient path
-    CUDA_CHECK(cudaSetDevice(h->device));
+    // Host arithmetic on 2 * 2N * nic numbers the caller already holds in host memory, as in the reference
+    // (infidelity_real is a pair of `dot`s on the final state, src/infidelity.jl:7-18); the gradient path forms the
+    // same two inner products on the device in k_terminal.
     const int B = (int)n_batch;
-    std::vector<double> out(B);
     const int N = h->N, N2 = h->N2;
     for (int b = 0; b < B; ++b) {  // O(2N*nic) work; objective-only calls are host side in the reference too
       double dR = 0, dT = 0;

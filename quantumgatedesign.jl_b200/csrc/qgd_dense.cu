@@ -859,7 +859,7 @@ void launch_dense_t(qgd_handle* h, const double* comb, double* uv, int ncols, in
 // Dense DMMA path of compute_derivatives! applicable?  (dense-classified problem, N a multiple of 32 up to 256, the 8
 // Taylor-column tiles fit the shared memory)
 bool dense_derivs_applicable(const qgd_handle* h, int m) {
-  if (getenv("QGD_DISABLE_DENSE_DMMA")) return false;
+  if (h->opt[QGD_OPT_DISABLE_DENSE_DMMA]) return false;
   if (h->fast_ok || h->dense_ops.empty() || h->N % 32 != 0 || h->N > 256 || m < 1 || m > 6) return false;
   return (size_t)(m + 1) * 8 * (2 * h->N + 4) * 8 <= h->prop.sharedMemPerBlockOptin;
 }
@@ -917,7 +917,7 @@ void launch_backward_dense_t(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs 
 bool prepare_dense_sweep(qgd_handle* h, const QgdDevProb& d, qgd::SweepArgs& a, qgd::DenseSweepArgs& ds, int& grid, size_t& smem,
                          size_t extra_smem, int ncols) {
   const int m = d.m, N = h->N, N2 = h->N2;
-  if (getenv("QGD_DISABLE_DENSE_SWEEP")) return false;
+  if (h->opt[QGD_OPT_DISABLE_DENSE_SWEEP]) return false;
   if (!dense_derivs_applicable(h, m) || h->Nc < 1) return false;
   smem = (size_t)(m + 1) * 8 * (N2 + 4) * 8 + extra_smem;
   if (smem + 1024 > h->prop.sharedMemPerBlockOptin) return false;
@@ -1002,8 +1002,8 @@ bool try_backward_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs
 
 // Infidelity + terminal condition of a dense problem (k_terminal_dense): all nic columns, 8 per CTA.
 bool try_terminal_dense(qgd_handle* h, const QgdDevProb& d, const qgd::SweepArgs& a_in) {
-  if (getenv("QGD_DENSE_TERMINAL_GENERIC")) return false;  // one warp per control vector (k_terminal)
-  const int seq = getenv("QGD_DENSE_TERMINAL_PARALLEL") ? 0 : 1;
+  if (h->opt[QGD_OPT_DENSE_TERMINAL] == 2) return false;  // one warp per control vector (k_terminal)
+  const int seq = h->opt[QGD_OPT_DENSE_TERMINAL] == 1 ? 0 : 1;
   qgd::SweepArgs a = a_in;
   qgd::DenseSweepArgs ds{};
   int grid = 0;

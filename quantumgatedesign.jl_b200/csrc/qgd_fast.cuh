@@ -37,6 +37,20 @@ namespace qgd {
 // Per-kernel code-shape switches of the blocked orthogonalisation, chosen by measurement:
 // bit 0 = the three basis tiers share one copy of the block arithmetic (smaller code: the adjoint kernel's hot
 // loop then fits the 32 KB instruction cache), bit 1 = block reduction through shared memory instead of shuffles.
+// Two-pass super-blocks (QGD_GS_SUPER = S, a multiple of 8; 0 = the one-pass blocks above, the default).  The S
+// coefficients of a super-block come from the same vector; pass 1 streams the basis once for the dot products, pass 2
+// streams it again for the updates: one dependent reduction chain per S vectors instead of one per 8.
+// tools/gs_block_experiment.py measures on the CPU oracle that widths from 8 to the whole basis leave every GMRES
+// iteration count of the C2 problem unchanged (tolerances 1e-12 .. 1e-15), so the numerics would allow it -- but
+// MEASURED ON B200 (round 2, profiles/r02_gs_superblock.txt) it is SLOWER at every width: 324 vs 388 evals/s at batch
+// 592 and 411 vs 337 ms for a single evaluation (S = 32, 64, 128 alike).  A warp issues in order, so the load ->
+// dots -> transposition chain of each group of 8 is exposed twice (once per pass) unless the groups are software-
+// pipelined, and that needs the partials of a whole super-block (64 registers) or one transposition buffer per group
+// (8 KB of shared memory per warp), neither of which exists beside the register-resident operators and the Krylov
+// tiers.  Kept compiled out as the record of the experiment.
+#ifndef QGD_GS_SUPER
+#define QGD_GS_SUPER 0
+#endif
 #ifndef QGD_FWD_VARIANT
 #define QGD_FWD_VARIANT 2
 #endif
@@ -166,9 +180,11 @@ struct FastCtx {
   double2* Vg;    // global            Krylov basis, tail (vector i >= KT+KS at (i-KT-KS)*32*EL)
   double* Rg;     // global            packed upper-triangular R: column j at j(j+1)/2
 };
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, bool STRICT = false>
 __host__ __device__ constexpr int fast_fixed_doubles(int N2) {
 #if QGD_COMPACT_SMEM
+  // strict kernels (progressive Givens): xs (+ gKs, gSs aliased) + cv + nullv + rot + g
+  if (STRICT) return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
   // xs (+ g, gKs, gSs aliased) + cv + nullv + hcol
   return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + (N2 + 2 + 8);
 #else
@@ -785,6 +801,68 @@ __device__ __forceinline__ void gs_orthogonalize(const FastCtx<EL>& c, int k, Ve
   }
 }
 
+// ---- two-pass super-block orthogonalisation (QGD_GS_SUPER) ------------------------------------------------
+// This lane's share of the transposed partial sums: value q = lane / 4, quarter s = lane % 4 (sum over the lanes
+// 4 t + s).  Same swizzled layout as block_allsum8_smem.
+__device__ __forceinline__ double transpose_partials8(const double (&p)[8], double* T, int lane) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) T[32 * q + (lane ^ (4 * (q & 3)))] = p[q];
+  __syncwarp();
+  const int qv = lane >> 2, s = lane & 3;
+  const double* row = T + 32 * qv + s;
+  const int sw = qv & 3;
+  double a[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) a[t] = row[4 * (t ^ sw)];
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+template <int EL>
+__device__ __forceinline__ void gs_load_group(const FastCtx<EL>& c, int i0, Vec<EL> (&vb)[8]) {
+  if (i0 < c.KT) gs_load_block<EL, 8, 0>(c, i0, vb);
+  else if (i0 < c.KT + c.KS) gs_load_block<EL, 8, 1>(c, i0, vb);
+  else gs_load_block<EL, 8, 2>(c, i0, vb);
+}
+
+template <int EL, int SUPER>
+__device__ __forceinline__ void gs_orthogonalize_super(const FastCtx<EL>& c, int k, Vec<EL>& w) {
+  static_assert(SUPER % 8 == 0 && SUPER >= 8, "super-block width");
+  double* T = reinterpret_cast<double*>(c.xs);
+  const int lane = c.lane;
+#pragma unroll 1
+  for (int s0 = 0; s0 < k; s0 += SUPER) {
+    const int s1 = min(k, s0 + SUPER);
+    // pass 1: h_i = <v_i, w> for the whole super-block from the same w
+#pragma unroll 1
+    for (int i0 = s0; i0 < s1; i0 += 8) {
+      Vec<EL> vb[8];
+      gs_load_group<EL>(c, i0, vb);
+      double h[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] = vdot_local<EL>(vb[q], w);
+      __syncwarp();  // the previous group's partials have been read
+      const double r = transpose_partials8(h, T, lane);
+      double c0, c1;
+      dmma884(c0, c1, 1.0, r);  // lane l: totals of values 2(l%4), 2(l%4)+1
+      if (lane < 4) reinterpret_cast<double2*>(c.hcol + i0)[lane] = make_double2(c0, c1);
+    }
+    __syncwarp();
+    // pass 2: w -= sum_i h_i v_i
+#pragma unroll 1
+    for (int i0 = s0; i0 < s1; i0 += 8) {
+      Vec<EL> vb[8];
+      gs_load_group<EL>(c, i0, vb);
+      double h[8];
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) { const double2 t = reinterpret_cast<const double2*>(c.hcol + i0)[q >> 1]; h[q] = t.x; h[q + 1] = t.y; }
+      const int nb = k - i0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < nb) vaxpy(w, -h[q], vb[q]);
+    }
+  }
+}
+
 // ---- asynchronous 8-byte copies L2 -> shared memory (cp.async, SASS LDGSTS) -----------------------------
 __device__ __forceinline__ void cp8(double* dst_smem, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -1061,7 +1139,8 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
       continue;
     }
     precond_fast<EL, NC>(R, w);  // expand!
-    gs_orthogonalize<EL, BLK, VARIANT>(c, k, w);
+    if constexpr (QGD_GS_SUPER > 0 && BLK == 8) { __syncwarp(); gs_orthogonalize_super<EL, QGD_GS_SUPER>(c, k, w); }
+    else gs_orthogonalize<EL, BLK, VARIANT>(c, k, w);
     // ||w||^2 and the null-vector recurrence <nullvec[0..k), H[0..k, k-1]> (update_residual!)
     double dpart = 0.0, hreg[CHK];
 #pragma unroll
@@ -1118,10 +1197,10 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
   return it;
 }
 
-template <int EL, int NC, int VARIANT, class OP>
+template <int EL, int NC, int VARIANT, bool STRICT, class OP>
 __device__ __forceinline__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b,
                                           double tol, int restart, int maxiter) {
-  if constexpr (QGD_MGS_BLOCK > 1) return gmres_fast_blocked<EL, NC, VARIANT, OP>(c, R, op, x, b, tol, restart, maxiter);
+  if constexpr (QGD_MGS_BLOCK > 1 && !STRICT) return gmres_fast_blocked<EL, NC, VARIANT, OP>(c, R, op, x, b, tol, restart, maxiter);
   else return gmres_fast_strict<EL, NC, OP>(c, R, op, x, b, tol, restart, maxiter);
 }
 
@@ -1164,11 +1243,16 @@ __device__ __forceinline__ void vload_cg(Vec<EL>& a, const double* p, int N, int
     a.v[e] = ok ? __ldcg(p + N + r) : 0.0;
   }
 }
-__device__ __forceinline__ void wait_segment(const int* progress, int seg, int lane) {
+__device__ __forceinline__ void wait_segment(const int* progress, int seg, int lane, int* err) {
   if (lane == 0) {
     const volatile int* f = progress;
     unsigned spins = 0;
-    while (*f < seg && ++spins < (1u << 27)) __nanosleep(256);  // the bound only turns a logic error into wrong numbers instead of a hang
+    // The ticket order rules out a deadlock (the previous segment was drawn earlier, so it is finished or running on
+    // a resident warp); the bound (about half a minute) only keeps a logic error or a wedged device from hanging the
+    // process: the sweep then continues with an unpublished state and raises the error word, which every host entry
+    // point checks after the sweeps (QGD_ESTATE) -- wrong numbers never leave the library silently.
+    while (*f < seg && ++spins < (1u << 27)) __nanosleep(256);
+    if (*f < seg) atomicExch(err, 1);
   }
   __syncwarp();
   __threadfence();
@@ -1189,7 +1273,7 @@ __device__ __forceinline__ void load_cv_fast(const FastCtx<EL>& c, const double*
 
 // shared-memory carve-up: [16 bytes: TMEM address slot][warp regions]; each region = fixed part + KS basis
 // vectors (+ extra doubles)
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, bool STRICT = false>
 __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra,
                                                      uint32_t tmem_base) {
   FastCtx<EL> c;
@@ -1206,9 +1290,15 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
 #if QGD_COMPACT_SMEM
   static_assert(FastCtx<EL>::kRingDoubles >= 64 * EL + 2, "g (2N + 2 doubles) aliases the gather buffer");
-  c.rot = nullptr; c.hcol = w; c.sub = nullptr; w += d.N2 + 2 + 8;
-  c.nullv = w; w += d.N2 + 2;
-  c.g = reinterpret_cast<double*>(c.xs);
+  if constexpr (STRICT) {
+    c.rot = reinterpret_cast<double2*>(w); c.hcol = w; c.sub = w + d.N2 + 10; w += 2 * (d.N2 + 2 + 8);
+    c.nullv = w; w += d.N2 + 2;
+    c.g = w; w += d.N2 + 2;
+  } else {
+    c.rot = nullptr; c.hcol = w; c.sub = nullptr; w += d.N2 + 2 + 8;
+    c.nullv = w; w += d.N2 + 2;
+    c.g = reinterpret_cast<double*>(c.xs);
+  }
 #else
   c.rot = reinterpret_cast<double2*>(w); c.hcol = w; c.sub = w + d.N2 + 10; w += 2 * (d.N2 + 2 + 8);
   c.nullv = w; w += d.N2 + 2;
@@ -1223,12 +1313,12 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, bool STRICT>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra, tmem_base);
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT>(d, a, smem, &extra, tmem_base);
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2;
   RegOps<EL, NC> R;
@@ -1261,7 +1351,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
         x.v[e] = r < N ? d.v0[r + (size_t)N * col] : 0.0;
       }
     } else {
-      wait_segment(a.progress + item, seg, lane);
+      wait_segment(a.progress + item, seg, lane, a.err);
       vload_cg(x, carry, N, lane);
     }
     load_cv_fast<EL, M, NC>(c, cvb + (size_t)n0 * cv_stride);
@@ -1273,7 +1363,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
       if (n == d.nsteps) break;
       load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n + 1) * cv_stride);              // implicit part uses t_{n+1}
       x = guess;
-      const int it = gmres_fast<EL, NC, QGD_FWD_VARIANT>(c, R, op, x, rhs, d.abstol, N2, N2);
+      const int it = gmres_fast<EL, NC, QGD_FWD_VARIANT, STRICT>(c, R, op, x, rhs, d.abstol, N2, N2);
       if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
     }
     vstore(x, carry, N, lane);
@@ -1334,13 +1424,13 @@ __device__ __forceinline__ void accumulate_grad_fast(int lane, int P, const QgdD
   }
 }
 
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, bool STRICT>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
                                                                                const QgdDevControl* __restrict__ ctrls) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC>(d, a, smem, &extra, tmem_base);
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT>(d, a, smem, &extra, tmem_base);
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2, Nt = d.nsteps + 1, P = d.P;
   RegOps<EL, NC> R0;
@@ -1388,7 +1478,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
       if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, lane);
     } else {
-      wait_segment(a.progress + item, seg, lane);
+      wait_segment(a.progress + item, seg, lane, a.err);
 #if !QGD_COMPACT_SMEM
       for (int t = lane; t < P; t += 32) gacc[t] = __ldcg(gcol + t);
 #endif
@@ -1481,7 +1571,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
           rhs.v[e] = fma(fsc, R.wv[e] * w0.v[e], rhs.v[e]);
         }
         // x0 = lambda_{n+1} (forward_evolution.jl:450)
-        const int it = gmres_fast<EL, NC, QGD_BWD_VARIANT>(c, R, op, lam, rhs, d.abstol, N2, N2);
+        const int it = gmres_fast<EL, NC, QGD_BWD_VARIANT, STRICT>(c, R, op, lam, rhs, d.abstol, N2, N2);
         if (lam0) vstore(lam, lam0 + (size_t)N2 * n, N, lane);
         if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
       }

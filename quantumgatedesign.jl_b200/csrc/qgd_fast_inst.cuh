@@ -25,7 +25,7 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   // tensor-memory tier: warps w and w + 4 of a CTA share a lane quarter, so each gets 512 / groups columns;
   // a vector takes 4 * el columns.  Allocation must be a power of two >= 32 columns.
   const int groups = (L.wpc + 3) / 4;
-  L.kt = restart >= 2 && getenv("QGD_DISABLE_TMEM") == nullptr ? std::min(restart + 1, (512 / groups) / (4 * el)) : 0;
+  L.kt = restart >= 2 && !h->opt[QGD_OPT_DISABLE_TMEM] ? std::min(restart + 1, (512 / groups) / (4 * el)) : 0;
   L.tmem_cols = 0;
   if (L.kt > 0) {
     int need = groups * L.kt * 4 * el, pow2 = 32;
@@ -60,13 +60,14 @@ void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, Sw
   h->d_V.reserve(v_bytes + warps * a.h_stride * 8);
   a.Vws = h->d_V.as<double>();
   a.Hws = reinterpret_cast<double*>(h->d_V.as<unsigned char>() + v_bytes);
-  h->d_counter.reserve(64);
-  CUDA_CHECK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+  ensure_counter(h);
+  CUDA_CHECK(cudaMemsetAsync(h->d_counter.p, 0, 4, h->stream));  // ticket counter; the error word behind it is sticky
   a.work_counter = h->d_counter.as<unsigned int>();
+  a.err = h->d_counter.as<int>() + 1;
   // time-sliced tickets: about 24 segments per column, published through d_progress
   const size_t items = (size_t)a.B * h->ncol;
   const int nsteps = (int)h->nsteps;
-  a.seg_steps = getenv("QGD_SEG_STEPS") ? std::max(1, atoi(getenv("QGD_SEG_STEPS"))) : std::max(1, (nsteps + 23) / 24);
+  a.seg_steps = h->opt[QGD_OPT_SEG_STEPS] > 0 ? (int)h->opt[QGD_OPT_SEG_STEPS] : std::max(1, (nsteps + 23) / 24);
   h->d_progress.reserve(std::max<size_t>(items, 1) * 4);
   CUDA_CHECK(cudaMemsetAsync(h->d_progress.p, 0, std::max<size_t>(items, 1) * 4, h->stream));
   a.progress = h->d_progress.as<int>();
@@ -87,10 +88,10 @@ void launch_sweep(qgd_handle* h, void (*kernel)(KArgs...), const FastCfg& L, Arg
   cfg.dynamicSmemBytes = L.smem; cfg.stream = h->stream;
   cudaLaunchAttribute at[1];
   int n = 0;
-  const char* env = getenv("QGD_L2_PERSIST");
+
   const size_t carve = (size_t)std::max(h->prop.persistingL2CacheMaxSize, 0);
   const size_t max_win = (size_t)std::max(h->prop.accessPolicyMaxWindowSize, 0);
-  if (env && atoi(env) == 1 && carve > 0 && max_win > 0 && h->d_V.cap > 0) {
+  if (h->opt[QGD_OPT_L2_PERSIST] == 1 && carve > 0 && max_win > 0 && h->d_V.cap > 0) {
     if (!h->l2_carved) {
       CUDA_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
       h->l2_carved = true;
@@ -109,18 +110,18 @@ void launch_sweep(qgd_handle* h, void (*kernel)(KArgs...), const FastCfg& L, Arg
   h->stats.kernel_launches++;
 }
 
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, bool STRICT>
 void launch_forward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
-  FastCfg L = plan_fast(h, k_forward_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)a.B * d.ncol, 0, d.N2);
+  FastCfg L = plan_fast(h, k_forward_fast<EL, M, NC, STRICT>, fast_fixed_doubles<EL, M, NC, STRICT>(d.N2), EL, (size_t)a.B * d.ncol, 0, d.N2);
   ensure_krylov_fast(h, L, EL, d.N2, a);
-  launch_sweep(h, k_forward_fast<EL, M, NC>, L, d, a);
+  launch_sweep(h, k_forward_fast<EL, M, NC, STRICT>, L, d, a);
 }
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, bool STRICT>
 void launch_backward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   const int extra = QGD_COMPACT_SMEM ? 0 : d.P + 2 * M * NC;
-  FastCfg L = plan_fast(h, k_backward_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)a.B * d.ncol, extra, d.N2);
+  FastCfg L = plan_fast(h, k_backward_fast<EL, M, NC, STRICT>, fast_fixed_doubles<EL, M, NC, STRICT>(d.N2), EL, (size_t)a.B * d.ncol, extra, d.N2);
   ensure_krylov_fast(h, L, EL, d.N2, a);
-  launch_sweep(h, k_backward_fast<EL, M, NC>, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
+  launch_sweep(h, k_backward_fast<EL, M, NC, STRICT>, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
 }
 template <int EL, int M, int NC>
 void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, int ncols, const double* cv, int adjoint) {
@@ -136,8 +137,10 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
 
 }  // namespace
 
-#define QGD_FAST_CASE_FWD(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC>(h, d, a); return true; }
-#define QGD_FAST_CASE_BWD(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC>(h, d, a); return true; }
+#define QGD_FAST_CASE_FWD(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC, false>(h, d, a); return true; }
+#define QGD_FAST_CASE_BWD(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC, false>(h, d, a); return true; }
+#define QGD_FAST_CASE_FWD_S(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC, true>(h, d, a); return true; }
+#define QGD_FAST_CASE_BWD_S(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC, true>(h, d, a); return true; }
 #define QGD_FAST_CASE_DER(EL, M, NC) if (el == EL && nc == NC) { launch_derivs_fast_t<EL, M, NC>(h, d, a, uv, ncols, cv, adjoint); return true; }
 
 #define QGD_DEFINE_FAST_LAUNCHERS(M)                                                                                        \
@@ -150,4 +153,13 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
   bool launch_derivs_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc, double* uv, int ncols,          \
                                const double* cv, int adjoint) {                                                             \
     QGD_FAST_SHAPES(QGD_FAST_CASE_DER, M) return false;                                                                     \
+  }
+
+// The same sweeps with strict modified Gram-Schmidt (QGD_OPT_STRICT_MGS), in translation units of their own.
+#define QGD_DEFINE_FAST_LAUNCHERS_STRICT(M)                                                                                 \
+  bool launch_forward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                       \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_FWD_S, M) return false;                                                                   \
+  }                                                                                                                         \
+  bool launch_backward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                      \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_BWD_S, M) return false;                                                                   \
   }

@@ -81,9 +81,36 @@ struct qgd_handle {
   bool host_controls = false;     // some control is QGD_CONTROL_HOST_TABLE: only the qgd_*_tables entry points work
   bool tables_from_host = false;  // inside a qgd_*_tables call: d_cvals / d_table hold the caller's tables
   bool l2_carved = false;  // cudaLimitPersistingL2CacheSize set for the workspace window (qgd_fast_inst.cuh)
+  int64_t opt[16] = {0};   // qgd_set_option values, indexed by QGD_OPT_*
+  // multi-GPU (qgd_multi.cu): NCCL communicator over the handles that share one evaluation by columns
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  DevBuf d_pack, d_dots;   // [grad P*B | guard B] all-reduced at the end of an evaluation; [2][B] terminal inner products
+  int* d_err = nullptr;    // device error word of the sweeps (lives behind the ticket counter in d_counter)
+  std::vector<double> hist_pcof;  // the control vectors the resident history was computed for (history_precomputed check)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   qgd_stats_t stats{};
 };
+
+// [0] ticket counter of the sweep being launched, [1] sticky device error word (see wait_segment)
+inline void ensure_counter(qgd_handle* h) {
+  if (h->d_counter.cap) return;
+  h->d_counter.reserve(64);
+  CUDA_CHECK(cudaMemsetAsync(h->d_counter.p, 0, 64, h->stream));
+}
+
+// NCCL, bound at run time (qgd_multi.cu)
+namespace qgd_nccl {
+void set_library(const char* path);
+int version();
+void unique_id(unsigned char out[128]);
+void* init_rank(int nranks, int rank, const unsigned char id[128]);
+void init_all(void** comms, int n, const int* devices);
+void destroy(void* comm);
+void allreduce_sum(void* comm, double* buf, size_t n, cudaStream_t stream);
+void group_start();
+void group_end();
+}  // namespace qgd_nccl
 
 // Kernel launchers, one set per EL = levels per lane (instantiated in qgd_inst_el*.cu).
 #define QGD_DECLARE_LAUNCHERS(EL)                                                                                   \
@@ -106,7 +133,9 @@ QGD_DECLARE_LAUNCHERS(8)
   bool launch_forward_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                     \
   bool launch_backward_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                    \
   bool launch_derivs_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc, double* uv, int ncols, \
-                               const double* cv, int adjoint);
+                               const double* cv, int adjoint);                                                     \
+  bool launch_forward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);              \
+  bool launch_backward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);
 QGD_DECLARE_FAST_LAUNCHERS(1)
 QGD_DECLARE_FAST_LAUNCHERS(2)
 QGD_DECLARE_FAST_LAUNCHERS(3)

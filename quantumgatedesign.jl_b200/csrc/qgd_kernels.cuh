@@ -27,6 +27,8 @@ struct SweepArgs {
   unsigned int* work_counter;  // fast path: ticket queue head (zeroed before the launch)
   int seg_steps;         // fast path: time steps per ticket
   int* progress;         // fast path: [items] segments published per item (zeroed before the launch)
+  int* err;              // fast path: sticky device error word (1: a ticket waited for a segment that was never
+                         // published); the host entry points read it after the sweeps and return QGD_ESTATE
   double* carry;         // fast path, adjoint sweep: [2N][ncol][B] lambda between segments
   const double* cvals;   // [B][nsteps+1][2][m+1][Nc]
   double* history;       // [2N][1+m][nslots][ncol][B]
@@ -48,6 +50,8 @@ struct SweepArgs {
   double* terminal_out;    // [2N][nic][B]
   double* infidelity;      // [B]
   int* iters_term;         // [nic][B] or null
+  const double* dots_in;   // column sharding with the scalar exchange: [2][B] all-reduced <psi_N,R>, <psi_N,T>; the terminal
+  int term_col0, term_ncol;  // condition is then solved for the columns [term_col0, term_col0 + term_ncol) only
   // forced forward solves (generic kernels only)
   const double* forcing_in;    // eval_forward!(...; forcing): [2N][m][nsteps+1][ncol][B], or null
   const double* base_history;  // eval_grad_forced: unforced history [2N][1+m][nsteps+1][ncol]; item b = control parameter b,
@@ -251,18 +255,24 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_terminal(const __gri
   for (int b = blockIdx.x * wpc + warp; b < a.B; b += gridDim.x * wpc) {
     const double* psi = a.final_all + (size_t)N2 * d.nic * b;
     double dR = 0.0, dT = 0.0;
-    for (int col = 0; col < d.nic; ++col) {
-      Vec<EL> p, R;
-      vload(p, psi + (size_t)N2 * col, N, lane);
-      vload(R, a.target + (size_t)N2 * col, N, lane);
+    int tc0 = 0, tc1 = d.nic;
+    if (a.dots_in) {  // the two inner products over ALL columns arrive all-reduced; psi holds the owned columns only
+      dR = a.dots_in[2 * b]; dT = a.dots_in[2 * b + 1];
+      tc0 = a.term_col0; tc1 = a.term_col0 + a.term_ncol;
+    } else {
+      for (int col = 0; col < d.nic; ++col) {
+        Vec<EL> p, R;
+        vload(p, psi + (size_t)N2 * col, N, lane);
+        vload(R, a.target + (size_t)N2 * col, N, lane);
 #pragma unroll
-      for (int e = 0; e < EL; ++e) {
-        dR += p.u[e] * R.u[e] + p.v[e] * R.v[e];
-        dT += p.u[e] * R.v[e] - p.v[e] * R.u[e];  // T = [R_v; -R_u]
+        for (int e = 0; e < EL; ++e) {
+          dR += p.u[e] * R.u[e] + p.v[e] * R.v[e];
+          dT += p.u[e] * R.v[e] - p.v[e] * R.u[e];  // T = [R_v; -R_u]
+        }
       }
+      dR = warp_sum(dR);
+      dT = warp_sum(dT);
     }
-    dR = warp_sum(dR);
-    dT = warp_sum(dT);
     const double ness2 = (double)d.Ness * (double)d.Ness;
     if (lane == 0) a.infidelity[b] = 1.0 - (dR * dR + dT * dT) / ness2;
     load_cv(c, a.cvals + ((size_t)b * (d.nsteps + 1) + d.nsteps) * cv_stride);  // controls at t = tf
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA) k_terminal(const __gri
     vzero(x);
     const double sc = 2.0 / ness2;
     const int restart = N2 < 20 ? N2 : 20;
-    for (int col = 0; col < d.nic; ++col) {
+    for (int col = tc0; col < tc1; ++col) {
       Vec<EL> p, R, Ww, rhs;
       vload(p, psi + (size_t)N2 * col, N, lane);
       vload(R, a.target + (size_t)N2 * col, N, lane);

@@ -11,6 +11,12 @@ Two natural partitions:
   the final sums.  Each rank owns a contiguous block of columns: forward sweep, all-gather of the final states
   (2N x nic doubles per control vector), backward sweep, all-reduce of [grad; guard] (`ColumnShardedEvaluator`).
 
+`attach_library_communicator` is the product path for columns: it hands every rank's `backend.Handle` an NCCL
+communicator INSIDE libqgd_b200.so (qgd_comm_init_rank); `Handle.discrete_adjoint` / `discrete_adjoint_device` then run
+both exchanges on the device, on the sweep stream, and torch.distributed only distributes the 128-byte NCCL id.
+`ColumnShardedEvaluator` (round 1: host-staged collectives around the two-phase ABI) stays as the reference
+implementation of the exchange pattern the CPU tests exercise.
+
 The evaluators only need a *backend* with the two-phase interface of the C ABI
 (`adjoint_phase1(pcofs, order) -> (final_local, guard_local)`,
 `adjoint_phase2(target_real, final_all) -> (grad_local, infidelity)`, `set_column_shard(begin, count)`,
@@ -133,3 +139,21 @@ class PcofShardedEvaluator:
             infid[rb:rb + rc] = a[:, P]
             guard[rb:rb + rc] = a[:, P + 1]
         return dict(grad=grad, infidelity=infid, guard_penalty=guard)
+
+
+def attach_library_communicator(handle, group=None, get_unique_id=None):
+    """Column sharding with the collectives inside the library: rank 0 of `group` draws an NCCL unique id through the C
+    ABI (qgd_comm_get_unique_id), torch.distributed broadcasts the 128 bytes, every rank attaches the communicator to
+    its handle (qgd_comm_init_rank, collective), which also assigns the rank its column block.  Afterwards
+    `handle.discrete_adjoint(pcofs, target, order=...)` on every rank (same arguments) returns the complete gradient."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if get_unique_id is None:
+        from .backend import comm_unique_id as get_unique_id
+    box = [get_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    uid = box[0]
+    if not isinstance(uid, (bytes, bytearray)) or len(uid) != 128:
+        raise RuntimeError("NCCL unique id did not arrive")
+    handle.comm_init_rank(world, rank, bytes(uid))
+    return world, rank

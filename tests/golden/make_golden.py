@@ -27,6 +27,19 @@ def cases(q):
     c["cnot3_333_o8"] = q.configs.cnot3(nsteps=12, tf=12.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=6)
     c["cnot3_444_o8_short"] = q.configs.cnot3(nsteps=6, tf=6.0, gmres_tol=1e-14)
     c["dense_o10"] = q.configs.dense_random(N=6, Nc=2, nsteps=8, order=10, gmres_tol=1e-14, dt_norm=0.5)
+    # round 2: C1 at its stated size (examples/cnot2_optimization.jl: nsteps = 100, default GMRES tolerance 1e-10) and C2 at
+    # the tolerance the bench runs with (1e-12; every other parity case uses 1e-13 .. 1e-15)
+    c["c1_cnot2_full"] = q.configs.cnot2()
+    c["c2_cnot3_tol12"] = q.configs.cnot3(nsteps=60, tf=60.0, gmres_tol=1e-12)
+    return c
+
+
+def heavy_cases(q):
+    """Cases the oracle needs minutes for: generated once, checked on the GPU only (the CPU suite checks their inputs)."""
+    c = {}
+    # C4 in the middle: N = 256 dense, 16 columns = two lockstep column groups per control vector, 20 steps, order 10
+    c["c4_dense256_mid"] = q.configs.dense_random(N=256, nic=16, Nc=4, nsteps=20, order=10, gmres_tol=1e-13, dt_norm=1.0,
+                                                  n_basis=20, degree=8)
     return c
 
 
@@ -44,7 +57,10 @@ def main():
     import oracle as O
 
     q = load_package()
-    for name, (prob, controls, pcof, target, order) in cases(q).items():
+    todo = dict(cases(q))
+    if "--heavy" in sys.argv:
+        todo = heavy_cases(q)
+    for name, (prob, controls, pcof, target, order) in todo.items():
         ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
         hist = ref["history"]
         np.savez_compressed(

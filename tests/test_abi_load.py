@@ -33,7 +33,7 @@ def test_struct_layout_matches_header(q):
     assert ctypes.sizeof(A.qgd_matrix_t) == 64
     assert ctypes.sizeof(A.qgd_control_t) == 64
     assert ctypes.sizeof(A.qgd_problem_t) == 32 + 2 * 64 + 4 * 8 + 64 + 8 + 8 + 16 + 8 + 8
-    assert ctypes.sizeof(A.qgd_stats_t) == 56
+    assert ctypes.sizeof(A.qgd_stats_t) == 64
 
 
 def test_n_coeff_helpers(q):
@@ -54,6 +54,52 @@ def test_no_cpu_fallback_without_gpu(q):
     assert ei.value.code == -2  # QGD_ECUDA
     with pytest.raises(q.QGDError):
         q.discrete_adjoint(prob, controls, pcof, target, order=order)
+
+
+def test_plain_c_program_links_and_fails_loudly_without_gpu(q):
+    """tests/abi_c/abi_smoke.c links against libqgd_b200.so with gcc (no Python in between); on this CPU box qgd_create
+    returns QGD_ECUDA and the program says so -- the GPU suite runs the same binary through create -> eval -> destroy."""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_round2.py::test_c_program_drives_the_abi")
+    if not os.path.exists(q.backend.LIB_PATH):
+        q.backend.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "abi_c")])
+    r = subprocess.run([os.path.join(ROOT, "tests", "abi_c", "abi_smoke")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("OK (no device"), (r.stdout, r.stderr)
+
+
+def test_library_reads_no_environment_variables(q):
+    """Behaviour switches are ABI calls (qgd_set_option), not getenv."""
+    csrc = os.path.join(ROOT, "quantumgatedesign.jl_b200", "csrc")
+    for fn in os.listdir(csrc):
+        if fn.endswith((".cu", ".cuh", ".h")):
+            assert "getenv" not in open(os.path.join(csrc, fn)).read(), fn
+
+
+def test_handle_cache_key_is_content_based(q):
+    """the api's handle cache was keyed on id(prob) / id(control); CPython reuses ids of freed
+    objects, so a temporary problem could inherit a dead problem's device operators.  The key is now a content
+    fingerprint: distinct problems -> distinct keys, equal content -> equal key, mutable knobs excluded."""
+    keys = set()
+    for i in range(40):
+        prob = q.construct_rand_prob(4, 1, tf=1.0, nsteps=6, seed=1000 + i)
+        keys.add(q.backend.problem_key(prob, q.GRAPEControl(3, prob.tf)))
+        del prob
+    assert len(keys) == 40
+    p1 = q.construct_rand_prob(4, 1, tf=1.0, nsteps=6, seed=5)
+    p2 = q.construct_rand_prob(4, 1, tf=1.0, nsteps=6, seed=5)
+    c = q.GRAPEControl(3, 1.0)
+    assert q.backend.problem_key(p1, c) == q.backend.problem_key(p2, q.GRAPEControl(3, 1.0))
+    assert q.backend.problem_key(p1, c) != q.backend.problem_key(p1, q.GRAPEControl(4, 1.0))
+    assert q.backend.problem_key(p1, c) != q.backend.problem_key(p1, q.CarrierControl(q.GRAPEControl(3, 1.0), [0.0, 1.0]))
+    assert q.backend.problem_key(p1, q.CarrierControl(c, [0.0, 1.0])) != q.backend.problem_key(p1, q.CarrierControl(c, [0.0, 2.0]))
+    k = q.backend.problem_key(p1, c)
+    p1.nsteps = 12; p1.gmres_abstol = 1e-13  # mutable knobs of the reference's SchrodingerProb: re-synced per call, not part of the key
+    assert q.backend.problem_key(p1, c) == k
 
 
 def test_host_validation_mirrors_reference(q):

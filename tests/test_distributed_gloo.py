@@ -98,7 +98,15 @@ def _worker(rank, world, port, nic, B, q):
         ok_pcof = (np.allclose(allp["grad"], ref["grad"], rtol=1e-13, atol=1e-13)
                    and np.allclose(allp["infidelity"], ref["infidelity"], rtol=1e-13)
                    and np.allclose(allp["guard_penalty"], ref["guard_penalty"], rtol=1e-13))
-        q.put((rank, ev.begin, ev.count, bool(ok_cols), bool(ok_local), bool(ok_pcof)))
+        # in-library communicator: rank 0's NCCL id must reach every rank, each rank attaches with its own rank number
+        class _Handle:
+            def comm_init_rank(self, n_ranks, rk, uid):
+                self.args = (n_ranks, rk, uid)
+
+        hh = _Handle()
+        pkg.distributed.attach_library_communicator(hh, get_unique_id=lambda: bytes([rank + 1]) * 128)
+        ok_comm = hh.args == (world, rank, bytes([1]) * 128)
+        q.put((rank, ev.begin, ev.count, bool(ok_cols), bool(ok_local), bool(ok_pcof), bool(ok_comm)))
     finally:
         dist.destroy_process_group()
 
@@ -122,6 +130,7 @@ def test_two_rank_sharding_equals_single_rank(nic, B):
     for r in res:
         assert r[3], f"column-sharded result differs on rank {r[0]}"
         assert r[4] and r[5], f"pcof-sharded result differs on rank {r[0]}"
+        assert r[6], f"NCCL unique id of rank 0 did not reach rank {r[0]} / wrong rank number passed to the library"
 
 
 def test_partition_tiles_the_range(q):

@@ -263,11 +263,9 @@ def test_dense_256_levels_short(q, O):
     out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
     # the opt-in parallel terminal condition (every column from a zero guess, 8 columns per CTA) moves lambda_N by the GMRES
     # tolerance; this gradient is ~1e-10 in size (1/N_ess^2 with 2 of 256 columns), so that shows at 1e-9 relative here
-    os.environ["QGD_DENSE_TERMINAL_PARALLEL"] = "1"
-    try:
-        par = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
-    finally:
-        del os.environ["QGD_DENSE_TERMINAL_PARALLEL"]
+    h.set_option(q.backend.OPT_DENSE_TERMINAL, 1)
+    par = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+    h.set_option(q.backend.OPT_DENSE_TERMINAL, 0)
     assert h.stats()["fast_path_launches"] == 2  # forward and adjoint sweep on the tensor-core contraction
     ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
     assert rel(par["grad"][:, 0], ref["grad"]) < 1e-7
@@ -530,12 +528,10 @@ def test_dense_forward_sweep_tensor_core_vs_oracle(q, O, N, nic, order, nsteps, 
         assert rel(out["final_state"][:, :, b], ref_h[:, 0, -1, :]) < RTOL
         for j in range(order // 2 + 1):
             assert rel(out["history"][:, j, :, :, b], ref_h[:, j]) < RTOL
-    os.environ["QGD_DISABLE_DENSE_SWEEP"] = "1"
-    try:
-        gen = h.eval_forward(pcs, order=order)
-        assert h.stats()["fast_path_launches"] == 0
-    finally:
-        del os.environ["QGD_DISABLE_DENSE_SWEEP"]
+    h.set_option(q.backend.OPT_DISABLE_DENSE_SWEEP, 1)
+    gen = h.eval_forward(pcs, order=order)
+    assert h.stats()["fast_path_launches"] == 0
+    h.set_option(q.backend.OPT_DISABLE_DENSE_SWEEP, 0)
     assert np.abs(out["iters"] - gen["iters"]).max() <= 1
     assert rel(out["history"], gen["history"]) < 1e-11
     h.close()
@@ -584,19 +580,15 @@ def test_dense_adjoint_sweep_tensor_core_vs_oracle(q, O, N, nic, order, nsteps, 
         assert rel(out["lambda_history"][:, 0, :, :, b], ref["lambda_history"][:, 0]) < 1e-9
         assert np.abs(out["iters_term"][:, b] - ref["iters_term"]).max() <= 1  # the reference's carried initial guess
     # opt-in parallel terminal condition (every column from a zero guess): lambda_N agrees to the GMRES tolerance
-    os.environ["QGD_DENSE_TERMINAL_PARALLEL"] = "1"
-    try:
-        par = h.discrete_adjoint(pcs, tgt, order=order, want_iters=True)
-    finally:
-        del os.environ["QGD_DENSE_TERMINAL_PARALLEL"]
+    h.set_option(q.backend.OPT_DENSE_TERMINAL, 1)
+    par = h.discrete_adjoint(pcs, tgt, order=order, want_iters=True)
+    h.set_option(q.backend.OPT_DENSE_TERMINAL, 0)
     assert par["iters_term"].min() >= 1 and rel(par["grad"], out["grad"]) < 1e-7
     assert np.array_equal(par["infidelity"], out["infidelity"])
-    os.environ["QGD_DISABLE_DENSE_SWEEP"] = "1"
-    try:
-        gen = h.discrete_adjoint(pcs, tgt, order=order, want_iters=True)
-        assert h.stats()["fast_path_launches"] == 0
-    finally:
-        del os.environ["QGD_DISABLE_DENSE_SWEEP"]
+    h.set_option(q.backend.OPT_DISABLE_DENSE_SWEEP, 1)
+    gen = h.discrete_adjoint(pcs, tgt, order=order, want_iters=True)
+    assert h.stats()["fast_path_launches"] == 0
+    h.set_option(q.backend.OPT_DISABLE_DENSE_SWEEP, 0)
     assert rel(out["grad"], gen["grad"]) < 1e-10
     assert np.abs(out["iters_adj"] - gen["iters_adj"]).max() <= 1
     h.close()

@@ -1,0 +1,285 @@
+"""GPU parity tests added in round 2 (all through the C ABI):
+
+* strict modified Gram-Schmidt as a RUN-TIME option of the shipped library (QGD_OPT_STRICT_MGS): GMRES iteration
+  counts EQUAL to the oracle's in every solve, at full C2 size too;
+* the timed entry point of bench.py, qgd_discrete_adjoint_device (device buffers in and out), against the host
+  entry point (bit for bit) and against the oracle;
+* the bench tolerance (1e-12), C1 at its stated size, a mid-size C4 (N = 256, two column groups, 20 steps) against
+  committed oracle fixtures;
+* option / state errors of the ABI, the handle cache of the Python api with many short-lived problems;
+* multi-GPU inside the library: communicator of one rank on one GPU (the collective code path), and -- when the box has
+  two GPUs -- column sharding through qgd_init_multi_gpu against the single-handle result.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def golden(name):
+    return np.load(os.path.join(HERE, "golden", name + ".npz"))
+
+
+# ---- strict MGS at run time --------------------------------------------------------------------------------------
+def _fast_cases(q):
+    return {
+        "cnot2": q.configs.cnot2(nsteps=20, tf=20.0, gmres_tol=1e-14),
+        "cnot3_333": q.configs.cnot3(nsteps=12, tf=12.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=6),
+        "cnot3_444_short": q.configs.cnot3(nsteps=6, tf=6.0, gmres_tol=1e-14),
+        "cnot3_444_tol15": q.configs.cnot3(nsteps=10, tf=10.0, gmres_tol=1e-15),
+    }
+
+
+@pytest.mark.parametrize("name", ["cnot2", "cnot3_333", "cnot3_444_short", "cnot3_444_tol15"])
+def test_strict_mgs_option_gives_equal_iteration_counts(q, O, name):
+    prob, controls, pcof, target, order = _fast_cases(q)[name]
+    h = q.Handle(prob, controls)
+    h.set_option(q.backend.OPT_STRICT_MGS, 1)
+    assert h.get_option(q.backend.OPT_STRICT_MGS) == 1
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+    assert h.stats()["fast_path_launches"] == 2, "strict mode must stay on the register-operator sweeps"
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert np.array_equal(out["iters_fwd"][:, :, 0], ref["iters_fwd"])
+    assert np.array_equal(out["iters_adj"][:, :, 0], ref["iters_adj"])
+    assert np.array_equal(out["iters_term"][:, 0], ref["iters_term"])
+    assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+    # and the default (blocked) orthogonalisation on the same handle: same numbers to the parity tolerance
+    h.set_option(q.backend.OPT_STRICT_MGS, 0)
+    blk = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+    assert rel(blk["grad"][:, 0], out["grad"][:, 0]) < RTOL
+    assert np.abs(blk["iters_fwd"] - out["iters_fwd"]).max() <= 1 and np.abs(blk["iters_adj"] - out["iters_adj"]).max() <= 1
+    h.close()
+
+
+def test_full_cnot3_order8_strict_mgs_exact_counts(q, O):
+    """BASELINE C2 at full size in strict mode: EVERY one of the 8 800 solves takes exactly the oracle's iterations."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=550, tf=550.0, gmres_tol=1e-14)
+    h = q.Handle(prob, controls)
+    h.set_option(q.backend.OPT_STRICT_MGS, 1)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    mism = int((out["iters_fwd"][:, :, 0] != ref["iters_fwd"]).sum() + (out["iters_adj"][:, :, 0] != ref["iters_adj"]).sum())
+    print("C2 full, strict MGS: total iterations", int(ref["iters_fwd"].sum() + ref["iters_adj"].sum()), "mismatching solves", mism,
+          "grad rel", rel(out["grad"][:, 0], ref["grad"]))
+    assert mism == 0
+    assert np.array_equal(out["iters_term"][:, 0], ref["iters_term"])
+    assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+    assert abs(out["guard_penalty"][0] - ref["guard_penalty"]) <= RTOL * abs(ref["guard_penalty"])
+    h.close()
+
+
+# ---- the timed entry point ---------------------------------------------------------------------------------------
+def test_device_entry_point_matches_host_entry_point_and_oracle(q, O):
+    import torch
+
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=12, tf=12.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=6)
+    P, B = len(pcof), 5
+    pcs = np.asfortranarray(np.stack([q.configs.cnot3_pcof(P, s) for s in range(B)], axis=1))
+    tgt = q.complex_to_real(target)
+    h = q.Handle(prob, controls, device=0)
+    host = h.discrete_adjoint(pcs, tgt, order=order)
+    d_pcof = torch.from_numpy(np.ascontiguousarray(pcs.T)).cuda()
+    d_tgt = torch.from_numpy(np.ascontiguousarray(tgt.T)).cuda()
+    d_grad = torch.full((B, P), float("nan"), dtype=torch.float64, device="cuda")
+    d_inf = torch.full((B,), float("nan"), dtype=torch.float64, device="cuda")
+    d_guard = torch.full((B,), float("nan"), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    h.discrete_adjoint_device(d_pcof.data_ptr(), B, d_tgt.data_ptr(), order, d_grad.data_ptr(), d_inf.data_ptr(), d_guard.data_ptr(),
+                              stream.cuda_stream)
+    h.synchronize(stream.cuda_stream)
+    g = d_grad.cpu().numpy().T
+    assert np.array_equal(g, host["grad"]), "device entry point differs from the host entry point"
+    assert np.array_equal(d_inf.cpu().numpy(), host["infidelity"]) and np.array_equal(d_guard.cpu().numpy(), host["guard_penalty"])
+    ref = O.discrete_adjoint(prob, controls, pcs[:, 3], target, order=order)
+    assert rel(g[:, 3], ref["grad"]) < RTOL
+    assert abs(d_inf[3].item() - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+    # the history of a device-side call never saw the control vectors on the host: history_precomputed must refuse it
+    with pytest.raises(q.QGDError) as e:
+        h.discrete_adjoint(pcs, tgt, order=order, history_precomputed=True)
+    assert e.value.code == -5
+    h.close()
+
+
+# ---- committed fixtures: bench tolerance, C1 full size, C4 mid size -------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_cnot2_full", "c2_cnot3_tol12"])
+def test_stated_size_and_bench_tolerance_fixtures(q, name):
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    prob, controls, pcof, target, order = mg.cases(q)[name]
+    g = golden(name)
+    for strict in (1, 0):
+        h = q.Handle(prob, controls)
+        h.set_option(q.backend.OPT_STRICT_MGS, strict)
+        out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+        h.close()
+        assert rel(out["grad"][:, 0], g["grad"]) < RTOL
+        assert abs(out["infidelity"][0] - float(g["infidelity"])) <= RTOL * abs(float(g["infidelity"]))
+        assert abs(out["guard_penalty"][0] - float(g["guard_penalty"])) <= RTOL * max(abs(float(g["guard_penalty"])), 1e-300)
+        df = out["iters_fwd"][:, :, 0] - g["iters_fwd"]
+        da = out["iters_adj"][:, :, 0] - g["iters_adj"]
+        if strict:
+            assert not df.any() and not da.any(), "strict MGS: iteration counts must equal the oracle's"
+        else:
+            assert np.abs(df).max() <= 1 and np.abs(da).max() <= 1
+            assert (df != 0).sum() + (da != 0).sum() <= max(1, (df.size + da.size) // 1000)
+        assert np.array_equal(out["iters_term"][:, 0], g["iters_term"])
+
+
+def test_c4_mid_size_dense_sweeps_vs_fixture(q):
+    """N = 256 dense, 16 columns (two lockstep column groups of the tensor-core sweeps), 20 steps, order 10, 4 control
+    operators: the state machine of k_forward_dense / k_backward_dense over a horizon, against the oracle fixture."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    prob, controls, pcof, target, order = mg.heavy_cases(q)["c4_dense256_mid"]
+    g = golden("c4_dense256_mid")
+    assert str(g["digest"]) == mg.input_digest(q, prob, controls, pcof, target)
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_history=True, want_iters=True)
+    assert h.stats()["fast_path_launches"] == 2, "C4 shape must run on the tensor-core sweeps"
+    h.close()
+    assert rel(out["grad"][:, 0], g["grad"]) < RTOL
+    assert abs(out["infidelity"][0] - float(g["infidelity"])) <= RTOL * abs(float(g["infidelity"]))
+    assert rel(out["history"][:, 0, -1, :, 0], g["final_state"]) < RTOL
+    df = out["iters_fwd"][:, :, 0] - g["iters_fwd"]
+    da = out["iters_adj"][:, :, 0] - g["iters_adj"]
+    assert np.abs(df).max() <= 1 and np.abs(da).max() <= 1
+    assert np.mean(df != 0) <= 0.05 and np.mean(da != 0) <= 0.05
+    assert np.abs(out["iters_term"][:, 0] - g["iters_term"]).max() <= 1
+
+
+# ---- ABI state / option errors -----------------------------------------------------------------------------------
+def test_option_and_state_errors(q):
+    prob, controls, pcof, target, order = q.configs.cnot2(nsteps=10, tf=10.0, gmres_tol=1e-13)
+    h = q.Handle(prob, controls)
+    with pytest.raises(q.QGDError) as e:
+        h.set_option(9999, 1)
+    assert e.value.code == -1
+    with pytest.raises(q.QGDError):
+        h.set_option(q.backend.OPT_STRICT_MGS, 7)
+    tgt = q.complex_to_real(target)
+    h.eval_forward(pcof, order=order, want_history=False, want_iters=False)
+    g0 = h.discrete_adjoint(pcof, tgt, order=order)["grad"]
+    # same control vector, resident history: fine and identical
+    h.eval_forward(pcof, order=order, want_history=False, want_iters=False)
+    g1 = h.discrete_adjoint(pcof, tgt, order=order, history_precomputed=True)["grad"]
+    assert np.array_equal(g0, g1)
+    # a DIFFERENT control vector must not be combined with the stale history (reference :118-140 takes the caller's array)
+    with pytest.raises(q.QGDError) as e:
+        h.discrete_adjoint(pcof * 1.01, tgt, order=order, history_precomputed=True)
+    assert e.value.code == -5
+    # re-syncing unchanged knobs keeps the history (what a binding does before every call)
+    h.eval_forward(pcof, order=order, want_history=False, want_iters=False)
+    h.set_nsteps(prob.nsteps)
+    h.set_gmres_tolerances(prob.gmres_abstol, prob.gmres_reltol)
+    g2 = h.discrete_adjoint(pcof, tgt, order=order, history_precomputed=True)["grad"]
+    assert np.array_equal(g0, g2)
+    h.close()
+
+
+def test_many_short_lived_problems_through_the_api(q, O):
+    """40 temporary problems through the cached api functions (the pattern of convergence.py: prob.copy() + fresh
+    controls per call): every call must see ITS operators, and the cache must stay bounded."""
+    q.backend.clear_handles()
+    for i in range(40):
+        prob = q.construct_rand_prob(4, 1, tf=1.0, nsteps=6, gmres_abstol=1e-14, gmres_reltol=1e-14, seed=1000 + i)
+        ctl = q.GRAPEControl(3, prob.tf)
+        pcof = np.random.default_rng(i).random(ctl.N_coeff)
+        hist = q.eval_forward(prob, ctl, pcof, order=4)
+        ref, _ = O.eval_forward(prob, ctl, pcof, order=4)
+        assert rel(hist[:, -1, :], q.real_to_complex(ref[:, 0, -1, :])) < RTOL, f"problem {i} was evaluated with stale operators"
+        del prob, ctl
+    assert len(q.backend._HANDLES) <= q.backend.HANDLE_CACHE_SIZE
+    q.backend.clear_handles()
+
+
+# ---- multi-GPU inside the library --------------------------------------------------------------------------------
+def test_communicator_of_one_rank_matches_plain_handle(q):
+    """The collective code path (NCCL all-reduces enqueued on the sweep stream) on one GPU: a communicator of ONE rank."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
+    tgt = q.complex_to_real(target)
+    pcs = np.stack([pcof, 0.5 * pcof], axis=1)
+    plain = q.Handle(prob, controls)
+    ref = plain.discrete_adjoint(pcs, tgt, order=order)
+    plain.close()
+    for exchange in (0, 1):
+        h = q.Handle(prob, controls)
+        h.comm_init_rank(1, 0, q.backend.comm_unique_id())
+        h.set_option(q.backend.OPT_TERMINAL_EXCHANGE, exchange)
+        out = h.discrete_adjoint(pcs, tgt, order=order)
+        assert h.stats()["collectives"] == 2
+        assert rel(out["grad"], ref["grad"]) < 1e-12
+        assert np.allclose(out["infidelity"], ref["infidelity"], rtol=1e-13, atol=0)
+        assert np.allclose(out["guard_penalty"], ref["guard_penalty"], rtol=1e-13, atol=1e-300)
+        h.comm_finalize()
+        again = h.discrete_adjoint(pcs, tgt, order=order)
+        assert np.array_equal(again["grad"], ref["grad"])
+        h.close()
+
+
+def _ngpu():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs on the box")
+@pytest.mark.parametrize("case", ["cnot3_333", "dense32"])
+def test_multi_gpu_column_sharding_matches_single_handle(q, case):
+    if case == "cnot3_333":
+        prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
+    else:
+        prob, controls, pcof, target, order = q.configs.dense_random(N=32, nic=11, Nc=2, nsteps=5, order=8, gmres_tol=1e-13, dt_norm=0.5)
+    tgt = q.complex_to_real(target)
+    pcs = np.stack([pcof, 0.5 * pcof, -0.3 * pcof], axis=1)
+    single = q.Handle(prob, controls, device=0)
+    ref = single.discrete_adjoint(pcs, tgt, order=order)
+    single.close()
+    n = min(_ngpu(), 4)
+    mg = q.backend.MultiGPU(prob, controls, n)
+    cols = mg.discrete_adjoint(pcs, tgt, order=order, shard=q.backend.SHARD_COLUMNS)
+    assert rel(cols["grad"], ref["grad"]) < 1e-12
+    assert np.allclose(cols["infidelity"], ref["infidelity"], rtol=1e-13, atol=0)
+    assert np.allclose(cols["guard_penalty"], ref["guard_penalty"], rtol=1e-12, atol=1e-300)
+    vecs = mg.discrete_adjoint(pcs, tgt, order=order, shard=q.backend.SHARD_CONTROL_VECTORS)
+    assert np.array_equal(vecs["grad"], ref["grad"]) and np.array_equal(vecs["infidelity"], ref["infidelity"])
+    if case == "cnot3_333":
+        mg.set_option(q.backend.OPT_TERMINAL_EXCHANGE, 1)  # two scalars per control vector instead of the final states
+        sc = mg.discrete_adjoint(pcs, tgt, order=order, shard=q.backend.SHARD_COLUMNS)
+        assert rel(sc["grad"], ref["grad"]) < 1e-9  # lambda_N of each rank's first column starts from a zero guess
+        assert np.allclose(sc["infidelity"], ref["infidelity"], rtol=1e-13, atol=0)
+    mg.close()
+
+
+# ---- the ABI from plain C ----------------------------------------------------------------------------------------
+def test_c_program_drives_the_abi(q):
+    """tests/abi_c/abi_smoke.c: create -> eval_forward -> discrete_adjoint (checked against finite differences of the
+    infidelity inside the C program) -> destroy, linked against libqgd_b200.so without Python in between."""
+    exe = os.path.join(HERE, "abi_c", "abi_smoke")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "abi_c")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "OK" in r.stdout

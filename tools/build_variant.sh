@@ -1,16 +1,26 @@
 #!/bin/bash
 # Build a variant of libqgd_b200.so with extra -D flags for A/B runs on the GPU box:
-#   tools/build_variant.sh <name> "<extra nvcc flags>"   ->  quantumgatedesign.jl_b200/csrc/variants/libqgd_b200_<name>.so
-# Select it at run time with QGD_B200_LIB=<path> (development only; the default library is csrc/libqgd_b200.so).
+#   tools/build_variant.sh <name> "<extra nvcc flags>" [units...]
+#       ->  quantumgatedesign.jl_b200/csrc/variants/libqgd_b200_<name>.so
+# Only the listed translation units (default: qgd_fast_m4, the order-8 register-operator sweeps the bench runs) are
+# recompiled with the flags; every other object comes from the default in-tree build (run `make` there first).
+# Select the variant at run time with QGD_B200_LIB=<path> (development only; the default library is csrc/libqgd_b200.so).
 set -e
-name=$1; extra=$2
+name=$1; extra=$2; shift 2 || true
+units=${@:-qgd_fast_m4}
 root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/quantumgatedesign.jl_b200/csrc
 bld=/tmp/qgd_variant_$name
-rm -rf $bld; mkdir -p $bld/quantumgatedesign.jl_b200 $root/quantumgatedesign.jl_b200/csrc/variants
-cp -r $root/include $bld/include
-mkdir -p $bld/quantumgatedesign.jl_b200/csrc
-cp $src/*.cu $src/*.cuh $src/*.h $src/Makefile $bld/quantumgatedesign.jl_b200/csrc/
-make -C $bld/quantumgatedesign.jl_b200/csrc -j12 NVCCFLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $extra" > $bld/make.log 2>&1 || { tail -20 $bld/make.log; exit 1; }
-cp $bld/quantumgatedesign.jl_b200/csrc/libqgd_b200.so $src/variants/libqgd_b200_$name.so
+rm -rf $bld; mkdir -p $bld $src/variants
+objs=""
+for o in $src/*.o; do
+  b=$(basename $o .o); skip=0
+  for u in $units; do [ "$b" = "$u" ] && skip=1; done
+  [ $skip = 0 ] && objs="$objs $o"
+done
+for u in $units; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $extra -Xptxas -v -c $src/$u.cu -o $bld/$u.o 2> $bld/$u.ptxas.log || { tail -20 $bld/$u.ptxas.log; exit 1; }
+  objs="$objs $bld/$u.o"
+done
+nvcc -shared -o $src/variants/libqgd_b200_$name.so $objs -lcudart 2>/dev/null
 echo "built $src/variants/libqgd_b200_$name.so"

@@ -17,11 +17,11 @@ rng = np.random.default_rng(3)
 pcs = np.stack([pcof] + [rng.random(len(pcof)) - 0.5 for _ in range(batch - 1)], axis=1)
 res = {}
 for name, env in (("dense", None), ("generic", "1")):
-    if env:
-        os.environ["QGD_DISABLE_DENSE_SWEEP"] = env
     if name == "generic" and len(sys.argv) > 4 and sys.argv[4] == "skip-generic":
         continue
     h = q.Handle(prob, controls)
+    if env:
+        h.set_option(q.backend.OPT_DISABLE_DENSE_SWEEP, 1)
     for rep in range(2):  # first call allocates
         out = h.eval_forward(pcs, order=order, want_history=False)
     st = h.stats()

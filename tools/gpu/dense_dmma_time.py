@@ -17,9 +17,9 @@ uv = np.zeros((512, m + 1, ncols), order="F")
 uv[:, 0, :] = rng.standard_normal((512, ncols))
 res = {}
 for label, env in (("dmma", None), ("generic", "1")):
-    if env:
-        os.environ["QGD_DISABLE_DENSE_DMMA"] = env
     h = q.Handle(prob, controls)
+    if env:
+        h.set_option(q.backend.OPT_DISABLE_DENSE_DMMA, 1)
     nc = ncols if label == "dmma" else min(ncols, 1184)
     best = 1e30
     for rep in range(3):
