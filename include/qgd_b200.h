@@ -312,6 +312,8 @@ int qgd_get_stats(qgd_handle_t *h, qgd_stats_t *out);
 /* Measured FP64 FMA throughput of this device in TFLOP/s (micro-benchmark kernel); the
  * roofline denominator MEASURED_PEAKS.json does not provide. */
 int qgd_measure_fp64_peak(int device, double *tflops);
+/* Same for the FP64 tensor cores (DMMA.8x8x4): the denominator for the dense sweeps. */
+int qgd_measure_dmma_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }

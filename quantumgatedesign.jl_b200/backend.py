@@ -29,6 +29,7 @@ EXPORTS = [
     "qgd_set_option", "qgd_get_option", "qgd_synchronize", "qgd_comm_set_nccl_library", "qgd_comm_get_unique_id",
     "qgd_comm_init_rank", "qgd_comm_finalize", "qgd_init_multi_gpu", "qgd_multi_n_gpus", "qgd_multi_handle",
     "qgd_multi_set_nsteps", "qgd_multi_set_gmres_tolerances", "qgd_multi_discrete_adjoint", "qgd_multi_destroy",
+    "qgd_measure_dmma_peak",
 ]
 
 # option keys of qgd_set_option (include/qgd_b200.h)
@@ -83,6 +84,7 @@ def lib():
                                               C.c_int32]
         L.qgd_get_stats.argtypes = [C.c_void_p, C.POINTER(_abi.qgd_stats_t)]
         L.qgd_measure_fp64_peak.argtypes = [C.c_int, c_double_p]
+        L.qgd_measure_dmma_peak.argtypes = [C.c_int, c_double_p]
         L.qgd_eval_forward_forced.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int32, C.c_int64, c_double_p,
                                               c_double_p, c_double_p, c_int64_p]
         L.qgd_eval_grad_forced.argtypes = [C.c_void_p, c_double_p, c_double_p, C.c_int32, c_double_p]
@@ -125,6 +127,12 @@ def _ip(a):
 def measure_fp64_peak(device: int = -1) -> float:
     out = np.zeros(1)
     _check(lib().qgd_measure_fp64_peak(device, _dp(out)))
+    return float(out[0])
+
+
+def measure_dmma_peak(device: int = -1) -> float:
+    out = np.zeros(1)
+    _check(lib().qgd_measure_dmma_peak(device, _dp(out)))
     return float(out[0])
 
 

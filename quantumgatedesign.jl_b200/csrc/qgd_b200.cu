@@ -117,6 +117,23 @@ __global__ void k_fp64_peak(double* out, int iters) {
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// FP64 tensor-core (DMMA.8x8x4) throughput micro-benchmark: 8 independent accumulator chains per warp.
+__global__ void k_dmma_peak(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * (threadIdx.x + 1);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace qgd
 
 namespace {
@@ -1459,6 +1476,40 @@ int qgd_measure_fp64_peak(int device, double* tflops) {
       float ms = 0;
       cudaEventElapsedTime(&ms, e0, e1);
       const double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+      if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+  });
+}
+
+// Measured FP64 tensor-core throughput (DMMA.8x8x4, 512 flop per warp instruction) in TFLOP/s: the roofline denominator of
+// the dense sweeps (qgd_dense.cu).
+int qgd_measure_dmma_peak(int device, double* tflops) {
+  return guarded([&]() {
+    require(tflops != nullptr, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw QgdError(QGD_ECUDA, "no CUDA device available");
+    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    const int threads = 256, blocks = prop.multiProcessorCount * 4, iters = 1 << 13;
+    double* d_out = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_out, (size_t)threads * blocks * 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+      cudaEventRecord(e0);
+      qgd::k_dmma_peak<<<blocks, threads>>>(d_out, iters);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double fl = 512.0 * 8.0 * (double)iters * (threads / 32) * blocks;
       if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -4,7 +4,9 @@
 
 #define QGD_MAX_OPS 9  // drift + up to 8 control operators
 #define QGD_MAX_M 10   // order <= 20 (the reference's coefficient() uses factorial(2m): Int64 limit)
-#define QGD_WARPS_PER_CTA 8
+#ifndef QGD_WARPS_PER_CTA
+#define QGD_WARPS_PER_CTA 8  // resident warps (= columns in flight) per SM of the sweep kernels
+#endif
 
 // Byte offsets (16-byte aligned) into the operator blob that every sweep CTA stages into shared
 // memory with one TMA bulk copy.  Operator k (0 = drift K_s/S_s, 1..Nc = control K_c/S_c) is stored

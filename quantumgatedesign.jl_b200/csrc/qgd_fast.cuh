@@ -455,6 +455,15 @@ __device__ __forceinline__ void basis_store(const FastCtx<EL>& c, int i, const V
 
 __device__ __forceinline__ int roff(int j) { return (j * (j + 1)) >> 1; }
 
+// Load from the packed Hessenberg / R workspace of the warp.  The workspace is L2-resident global memory at full batch
+// (cache-global: it is written by other lanes of the warp) and shared memory when few columns are in flight
+// (FastCfg::h_smem): a generic-address load serves both, the cache operator is a hint that shared memory ignores.
+__device__ __forceinline__ double hld(const double* p) {
+  double v;
+  asm volatile("ld.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // LinearAlgebra.givensAlgorithm for reals with one reciprocal square root instead of sqrt + two divisions
 __device__ __forceinline__ void givens_fast(double f, double g, double& cs, double& sn) {
   if (g == 0.0) { cs = 1.0; sn = 0.0; }
@@ -476,16 +485,16 @@ __device__ __forceinline__ void trsv_fast(const FastCtx<EL>& c, int width) {
   {
     const double* col = c.Rg + roff(width - 1);
 #pragma unroll
-    for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; cur[q] = i < width - 1 ? __ldcg(col + i) : 0.0; }
-    dcur = __ldcg(col + width - 1);
+    for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; cur[q] = i < width - 1 ? hld(col + i) : 0.0; }
+    dcur = hld(col + width - 1);
   }
   __syncwarp();
   for (int j = width - 1; j >= 0; --j) {
     if (j > 0) {
       const double* col = c.Rg + roff(j - 1);
 #pragma unroll
-      for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; nxt[q] = i < j - 1 ? __ldcg(col + i) : 0.0; }
-      dnxt = __ldcg(col + j - 1);
+      for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; nxt[q] = i < j - 1 ? hld(col + i) : 0.0; }
+      dnxt = hld(col + j - 1);
     }
     const double yj = c.g[j] * dcur;  // dcur = 1 / R[j][j]
     __syncwarp();
@@ -709,6 +718,23 @@ __device__ __forceinline__ void block_allsum8_smem(double (&p)[8], double* T, do
   for (int q = 0; q < 8; q += 2) { const double2 t = reinterpret_cast<const double2*>(slot)[q >> 1]; p[q] = t.x; p[q + 1] = t.y; }
 }
 
+// Same result with tensor-core reductions only (variant bit 2): per value one DMMA with a ones A operand sums the
+// 4-lane groups (lane l receives the sums of groups 2(l%4), 2(l%4)+1), their sum fed back as the A operand of a second
+// DMMA against ones sums the remaining four -- 16 independent, pipelined DMMA and 8 DADD per block, no shared-memory
+// round trip and no warp synchronisation; every lane ends up with all 8 totals.  The coefficients still have to reach
+// c.hcol (the Hessenberg column): lane 0 stores them.
+__device__ __forceinline__ void block_allsum8_dmma(double (&p)[8], double* slot, int lane) {
+  double t[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { double c0, c1; dmma884(c0, c1, 1.0, p[q]); t[q] = c0 + c1; }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { double d0, d1; dmma884(d0, d1, t[q], 1.0); p[q] = d0; }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) reinterpret_cast<double2*>(slot)[q >> 1] = make_double2(p[q], p[q + 1]);
+  }
+}
+
 // tcgen05.ld of N consecutive 32-bit columns of this warp's 32 TMEM lanes (issue only)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -771,7 +797,8 @@ __device__ __forceinline__ void gs_block(const FastCtx<EL>& c, int i0, int nb, c
   double h[BLK];
 #pragma unroll
   for (int q = 0; q < BLK; ++q) h[q] = vdot_local<EL>(vb[q], w);
-  if constexpr (BLK == 8 && (VARIANT & 2) != 0) block_allsum8_smem(h, reinterpret_cast<double*>(c.xs), c.hcol + i0, c.lane);
+  if constexpr (BLK == 8 && (VARIANT & 4) != 0) block_allsum8_dmma(h, c.hcol + i0, c.lane);
+  else if constexpr (BLK == 8 && (VARIANT & 2) != 0) block_allsum8_smem(h, reinterpret_cast<double*>(c.xs), c.hcol + i0, c.lane);
   else block_allsum<BLK>(h, c.hcol + i0, c.lane);
 #pragma unroll
   for (int q = 0; q < BLK; ++q)
@@ -896,7 +923,7 @@ __device__ __forceinline__ void qr_solve_fast(const CTX& c, int width, double be
   for (int s = 0; s < CH; ++s) {
     const int j = lane + 32 * s;
     colp[s] = c.Rg + hoff(j);
-    top[s] = j < width ? __ldcg(colp[s]) : 0.0;
+    top[s] = j < width ? hld(colp[s]) : 0.0;
   }
   double gcur = beta;
   for (int i = -D; i < width; ++i) {  // the first D trips only fill the ring (rows 1..D)
@@ -993,7 +1020,7 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
 #pragma unroll
     for (int s = S0; s < CH; ++s) {
       const int j = lane + 32 * s;
-      lo[s] = (s < nsl && j < width && r <= j + 1) ? __ldcg(colp[s] + r) : 0.0;
+      lo[s] = (s < nsl && j < width && r <= j + 1) ? hld(colp[s] + r) : 0.0;
     }
   };
   auto rotate = [&](int i, const double (&lo)[CH]) {
@@ -1043,7 +1070,7 @@ __device__ __forceinline__ void qr_backsub_phase(double (&gi)[CH], const double*
 #pragma unroll
     for (int q = 0; q <= S0; ++q) {
       const int i = lane + 32 * q;
-      col[q] = (j >= 0 && i < j) ? __ldcg(src + i) : 0.0;
+      col[q] = (j >= 0 && i < j) ? hld(src + i) : 0.0;
     }
   };
   auto step = [&](int j, const double (&col)[CH]) {
@@ -1079,7 +1106,7 @@ __device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double be
   for (int s = 0; s < CH; ++s) {
     const int j = lane + 32 * s;
     colp[s] = c.Rg + hoff(j);
-    top[s] = j < width ? __ldcg(colp[s]) : 0.0;
+    top[s] = j < width ? hld(colp[s]) : 0.0;
   }
   double gcur = beta;
   qr_rotation_phase<0, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
@@ -1141,6 +1168,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
     precond_fast<EL, NC>(R, w);  // expand!
     if constexpr (QGD_GS_SUPER > 0 && BLK == 8) { __syncwarp(); gs_orthogonalize_super<EL, QGD_GS_SUPER>(c, k, w); }
     else gs_orthogonalize<EL, BLK, VARIANT>(c, k, w);
+    if constexpr ((VARIANT & 4) != 0) __syncwarp();  // lane 0's coefficient stores (block_allsum8_dmma) before c.hcol is read
     // ||w||^2 and the null-vector recurrence <nullvec[0..k), H[0..k, k-1]> (update_residual!)
     double dpart = 0.0, hreg[CHK];
 #pragma unroll
@@ -1305,10 +1333,11 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   c.g = w; w += d.N2 + 2;
 #endif
   c.Vs = reinterpret_cast<double2*>(w); w += (size_t)a.ks * 2 * 32 * EL;
+  double* hs = w; w += a.h_smem_doubles;
   *extra = w;
   const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
   c.Vg = reinterpret_cast<double2*>(a.Vws + slot * a.v_stride);
-  c.Rg = a.Hws + slot * a.h_stride;
+  c.Rg = a.h_smem_doubles ? hs : a.Hws + slot * a.h_stride;
   return c;
 }
 

@@ -10,7 +10,7 @@
 namespace {
 using namespace qgd;
 
-struct FastCfg { int grid, threads, wpc, ks, kt, tmem_cols, warp_doubles; size_t smem; };
+struct FastCfg { int grid, threads, wpc, ks, kt, tmem_cols, warp_doubles, h_smem; size_t smem; };
 
 // One CTA per SM, all of its shared memory split between the warps; whatever is left after the fixed
 // per-warp arrays holds the resident part of the Krylov basis.
@@ -20,6 +20,7 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   const int sms = h->prop.multiProcessorCount;
   FastCfg L{};
   L.wpc = (int)std::min<size_t>(QGD_WARPS_PER_CTA, std::max<size_t>(1, (items + sms - 1) / sms));
+  if (h->opt[QGD_OPT_LATENCY_WARPS] > 0) L.wpc = (int)h->opt[QGD_OPT_LATENCY_WARPS];
   const int vec = 2 * 32 * el;
   const int base = (fixed_doubles + extra_doubles + 1) & ~1;
   // tensor-memory tier: warps w and w + 4 of a CTA share a lane quarter, so each gets 512 / groups columns;
@@ -36,12 +37,21 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   constexpr int blk = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 1;  // a Gram-Schmidt block never straddles two tiers
   L.kt = (L.kt / blk) * blk;
   const long per_warp = (long)((max_smem - 16) / 8 / L.wpc) & ~1L;
-  long ks = (per_warp - base) / vec;
+  // Few columns in flight (one or two warps per SM -- a single gradient evaluation, what optimize_gate asks for): the
+  // packed Hessenberg matrix of the warp fits into shared memory beside the whole Krylov basis, so the end-of-solve
+  // least squares reads shared memory instead of waiting an L2 round trip per rotation.
+  L.h_smem = 0;
+  {
+    const long hd = ((long)restart * (restart + 3) / 2 + 2 + 1) & ~1L;
+    const long want_vec = std::max(restart + 1 - L.kt, 0);
+    if (L.wpc <= 2 && restart >= 2 && per_warp - base - hd >= std::min<long>(want_vec, 16) * vec) L.h_smem = (int)hd;
+  }
+  long ks = (per_warp - base - L.h_smem) / vec;
   ks = std::min<long>(ks, std::max(restart + 1 - L.kt, 0));
   if (ks < 0) throw QgdError(QGD_EUNSUPPORTED, "fast path: shared memory too small for the per-warp state");
   L.ks = (int)(ks / blk) * blk;
   ks = L.ks;
-  L.warp_doubles = base + (int)ks * vec;
+  L.warp_doubles = base + (int)ks * vec + L.h_smem;
   L.threads = 32 * L.wpc;
   L.smem = 16 + (size_t)L.wpc * L.warp_doubles * 8;
   CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
@@ -73,7 +83,7 @@ void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, Sw
   a.progress = h->d_progress.as<int>();
   h->d_carry.reserve(std::max<size_t>(items, 1) * (size_t)h->N2 * 8);
   a.carry = h->d_carry.as<double>();
-  a.ks = L.ks; a.kt = L.kt; a.tmem_cols = L.tmem_cols;
+  a.ks = L.ks; a.kt = L.kt; a.tmem_cols = L.tmem_cols; a.h_smem_doubles = L.h_smem;
   a.warp_smem_doubles = L.warp_doubles;
 }
 
