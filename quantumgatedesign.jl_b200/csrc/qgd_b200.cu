@@ -556,6 +556,10 @@ bool try_backward_fast_default(qgd_handle* h, const QgdDevProb& d, const SweepAr
 bool try_backward_fast_strict(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   QGD_FAST_SWITCH(d.m, launch_backward_fast_strict, h, d, a, h->fast_el, h->Nc)
 }
+bool try_forward_fast_forced(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {  // forced solves: eval_forward!(...; forcing), eval_grad_forced
+  if (!fast_applicable(h, d.m)) return false;
+  QGD_FAST_SWITCH(d.m, launch_forward_fast_forced, h, d, a, h->fast_el, h->Nc)
+}
 // QGD_OPT_STRICT_MGS selects the strict modified Gram-Schmidt instantiation of the same sweeps
 bool try_forward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (!fast_applicable(h, d.m)) return false;
@@ -594,7 +598,8 @@ void run_forward(qgd_handle* h, const double* d_pcof, int B, int order, int64_t 
   if (want_iters) { h->d_iters_f.reserve((size_t)h->nsteps * h->ncol * B * 4); a.iters = h->d_iters_f.as<int>(); }
   a.forcing_in = d_forcing;
   CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
-  if (d_forcing || !(try_forward_fast(h, d, a) || try_forward_dense(h, d, a))) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
+  const bool done = d_forcing ? try_forward_fast_forced(h, d, a) : (try_forward_fast(h, d, a) || try_forward_dense(h, d, a));
+  if (!done) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
   CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
   h->hist_B = B; h->hist_order = order; h->hist_nsteps = h->nsteps; h->hist_save = save_every; h->hist_valid = d_forcing == nullptr;
 }
@@ -623,7 +628,7 @@ void run_forced_gradient_solves(qgd_handle* h, int order) {
   CUDA_CHECK(cudaStreamSynchronize(h->stream));  // `top` is a local
   a.theta_op = h->d_theta_op.as<int>();
   (void)m;
-  QGD_DISPATCH_EL(el, launch_forward, h, d, a);
+  if (!try_forward_fast_forced(h, d, a)) { QGD_DISPATCH_EL(el, launch_forward, h, d, a); }
 }
 
 // guard partials + (optionally) forcing array from the device-resident history

@@ -234,13 +234,66 @@ __device__ __forceinline__ void zsums(const RegOps<EL, NC>& R, const double2* xs
 
 // out = sum_j alpha_j w_j, w_0 = x, w_{j+1} = (1/(j+1)) sum_{i<=j} A_{j-i} w_i  (scatter form).
 // STEP: also guess = sum_j a_tay_j w_j and, if hist != nullptr, hist[:, j] = w_j.
-template <int EL, int M, int NC, bool STEP>
+// FORCE: the recursion carries a forcing, w_{j+1} = (1/(j+1)) (sum_{i<=j} A_{j-i} w_i + f_j)
+// (compute_derivatives!(...; forcing_matrix), reference src/hermite.jl:91-95).  f_j is either read from an explicit array
+// (eval_forward!(...; forcing), src/forward_evolution.jl:118-129) or formed on the fly for eval_grad_forced
+// (src/eval_grad_forced.jl:82-131) from the Taylor columns w_i of the unforced solution and the control basis table,
+//   f_j = sum_{i<=j} d/dtheta [p^(j-i)/(j-i)!] (K w_i)-part + d/dtheta [q^(j-i)/(j-i)!] (S w_i)-part
+// with K, S the control operator the parameter theta belongs to: the same scatter as the recursion itself, with the
+// basis-table entries of theta in the place of the control values and the history columns in the place of the w_i.
+struct FastForcing {
+  const double* arr;  // [2N][M] explicit forcing of this time level, or null
+  const double* hb;   // [2N][1+M] unforced Taylor columns of this time level (global), or null
+  const double* tp;   // tp[dd * P] = d/dtheta p^(dd)/dd! at this time level; tq likewise
+  const double* tq;
+  int P, kop;         // kop: index (0-based) of the control operator of theta
+};
+
+template <int EL, int M, int NC, bool STEP, bool FORCE = false>
 __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
-                                         Vec<EL>& out, const double* a_tay, Vec<EL>* guess, double* hist) {
+                                         Vec<EL>& out, const double* a_tay, Vec<EL>* guess, double* hist,
+                                         const FastForcing* F = nullptr) {
   const int lane = c.lane, N = c.N, N2 = c.N2;
   Vec<EL> acc[M + 1];
 #pragma unroll
   for (int j = 1; j <= M; ++j) vzero(acc[j]);
+  if constexpr (FORCE) {
+    if (F->arr) {
+#pragma unroll
+      for (int j = 0; j < M; ++j) vload_cg(acc[j + 1], F->arr + (size_t)j * N2, N, lane);
+    }
+    if (F->hb) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        Vec<EL> wi;
+        vload_cg(wi, F->hb + (size_t)i * N2, N, lane);
+        double2* xb = c.xs + (i & 1) * 32 * EL;
+        xs_store<EL>(xb, wi, lane);
+        __syncwarp();
+        ZS<EL, NC> z;
+        zsums<EL, NC>(R, xb, z);
+        double Ku[EL], Kv[EL], Su[EL], Sv[EL];
+#pragma unroll
+        for (int e = 0; e < EL; ++e) {
+          Ku[e] = z.Ku[e][0]; Kv[e] = z.Kv[e][0]; Su[e] = z.Su[e][0]; Sv[e] = z.Sv[e][0];
+#pragma unroll
+          for (int k = 1; k < NC; ++k)
+            if (k == F->kop) { Ku[e] = z.Ku[e][k]; Kv[e] = z.Kv[e][k]; Su[e] = z.Su[e][k]; Sv[e] = z.Sv[e][k]; }
+        }
+#pragma unroll
+        for (int j = i; j < M; ++j) {
+          const double pv = F->tp[(size_t)(j - i) * F->P], qv = F->tq[(size_t)(j - i) * F->P];
+#pragma unroll
+          for (int e = 0; e < EL; ++e) {
+            acc[j + 1].u[e] = fma(pv, Kv[e], fma(qv, Su[e], acc[j + 1].u[e]));
+            acc[j + 1].v[e] = fma(-pv, Ku[e], fma(qv, Sv[e], acc[j + 1].v[e]));
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
   Vec<EL> w = x;
   out = x;
   vscale(out, alpha[0]);
@@ -458,6 +511,29 @@ __device__ __forceinline__ int roff(int j) { return (j * (j + 1)) >> 1; }
 // Load from the packed Hessenberg / R workspace of the warp.  The workspace is L2-resident global memory at full batch
 // (cache-global: it is written by other lanes of the warp) and shared memory when few columns are in flight
 // (FastCfg::h_smem): a generic-address load serves both, the cache operator is a hint that shared memory ignores.
+__device__ __forceinline__ double2 hld2(const double* p) {  // 16-byte aligned pair
+  double2 v;
+  asm volatile("ld.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// Offset of column j (rows 0..j+1) of the packed Hessenberg matrix.  QGD_QR_ROWS4 = 1: every column starts on a 32-byte
+// boundary (its j + 2 entries padded to a multiple of 4), so that a lane walks down ITS column four rows -- one 32-byte
+// sector -- per request in the end-of-solve QR (qr_rotation_phase) instead of one row per request, with two groups in
+// flight.  MEASURED ON B200 (round 2, profiles/r02_kernel_variants.txt): 353 vs 385 evals/s at batch 592 (forward sweep
+// 760 vs 701 ms) and no change for a single evaluation -- a quarter of the scattered requests, but 24 more live registers
+// and a longer per-solve code path beside a GMRES loop that has to stay in the instruction cache.  Off by default.
+#ifndef QGD_QR_ROWS4
+#define QGD_QR_ROWS4 0
+#endif
+__device__ __host__ __forceinline__ int hpk(int j) {
+#if QGD_QR_ROWS4
+  // 4 * sum_{c<j} ceil((c+2)/4) = 4 * (S(j+4) - 1), S(n) = sum_{t<=n} floor(t/4) = 2q(q-1) + q(r+1), n = 4q + r
+  const int n = j + 4, q = n >> 2, r = n & 3;
+  return 4 * (2 * q * (q - 1) + q * (r + 1) - 1);
+#else
+  return (j * (j + 3)) >> 1;
+#endif
+}
 __device__ __forceinline__ double hld(const double* p) {
   double v;
   asm volatile("ld.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -922,7 +998,7 @@ __device__ __forceinline__ void qr_solve_fast(const CTX& c, int width, double be
 #pragma unroll
   for (int s = 0; s < CH; ++s) {
     const int j = lane + 32 * s;
-    colp[s] = c.Rg + hoff(j);
+    colp[s] = c.Rg + hpk(j);
     top[s] = j < width ? hld(colp[s]) : 0.0;
   }
   double gcur = beta;
@@ -988,7 +1064,7 @@ __device__ __forceinline__ void qr_solve_fast(const CTX& c, int width, double be
     const int jn = j - D;  // column to fetch now
     if (jn >= 0) {
       double* wcol = ring + ((jn & dmask) * RS) * 32;
-      const double* src = c.Rg + hoff(jn);
+      const double* src = c.Rg + hpk(jn);
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
         const int i = lane + 32 * q;
@@ -1015,6 +1091,7 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
   const int i0 = 32 * S0;
   if (i0 >= width) return;
   const int iend = min(width, i0 + 32);
+#if !QGD_QR_ROWS4
   double loA[CH], loB[CH];
   auto fetch = [&](double (&lo)[CH], int r) {  // row r of the owned columns j = lane + 32 s >= r - 1
 #pragma unroll
@@ -1023,6 +1100,7 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
       lo[s] = (s < nsl && j < width && r <= j + 1) ? hld(colp[s] + r) : 0.0;
     }
   };
+#endif
   auto rotate = [&](int i, const double (&lo)[CH]) {
     const double a = __shfl_sync(FULL_MASK, top[S0], i & 31);
     const double b = __shfl_sync(FULL_MASK, lo[S0], i & 31);  // H[i+1][i], the row of the pivot owner's own column
@@ -1042,6 +1120,45 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
     if (lane == 0) { dinv[i] = rr; g[i] = cs * gcur; }  // r_ii = cs a + sn b = 1 / rr
     gcur = -sn * gcur;
   };
+#if QGD_QR_ROWS4
+  // Rows in groups of four: the owned columns start 32-byte aligned, a lane fetches rows 4q..4q+3 of each of them with two
+  // 16-byte loads (ONE sector) and the next two groups are in flight while a group is being rotated -- a quarter of the
+  // scattered requests of the row-at-a-time version and 4 to 8 rotations of L2 latency hidden instead of 2.
+  double A[CH][4], B[CH][4];
+  auto fetch4 = [&](double (&buf)[CH][4], int gq) {  // rows 4 gq .. 4 gq + 3 of the owned columns j >= 4 gq - 1
+#pragma unroll
+    for (int s = S0; s < CH; ++s) {
+      const int j = lane + 32 * s;
+      if (s < nsl && j < width && 4 * gq <= j + 1) {
+        const double2 lo2 = hld2(colp[s] + 4 * gq), hi2 = hld2(colp[s] + 4 * gq + 2);
+        buf[s][0] = lo2.x; buf[s][1] = lo2.y; buf[s][2] = hi2.x; buf[s][3] = hi2.y;
+      } else {
+        buf[s][0] = buf[s][1] = buf[s][2] = buf[s][3] = 0.0;
+      }
+    }
+  };
+  auto rotate_group = [&](const double (&buf)[CH][4], int gq) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 4 * gq + e - 1;  // rotation i uses row i + 1
+      if (i >= i0 && i < iend) {
+        double lo[CH];
+#pragma unroll
+        for (int s = 0; s < CH; ++s) lo[s] = buf[s][e];
+        rotate(i, lo);
+      }
+    }
+  };
+  int gq = (i0 + 1) >> 2;
+  fetch4(A, gq);
+  fetch4(B, gq + 1);
+  for (; 4 * gq <= iend; gq += 2) {
+    rotate_group(A, gq);
+    fetch4(A, gq + 2);
+    rotate_group(B, gq + 1);
+    fetch4(B, gq + 3);
+  }
+#else
   // two rows ahead, hand-unrolled.  Measured: prefetching 1 / 2 / 4 rows ahead gives 382 / 388 / 343
   // evals/s, a generic depth-D loop at D = 2 gives 377, L1-cached loads 382 -- the kernels are that sensitive to the size
   // and layout of the per-solve code.
@@ -1055,6 +1172,7 @@ __device__ __forceinline__ void qr_rotation_phase(double (&top)[CH], double* con
       fetch(loB, i + 4);
     }
   }
+#endif
 }
 
 // back substitution R y = g for the rows [32 S0, 32 S0 + 32) of the pivot: right-hand side rows i = lane + 32 q in
@@ -1066,7 +1184,7 @@ __device__ __forceinline__ void qr_backsub_phase(double (&gi)[CH], const double*
   const int j_hi = min(width, j_lo + 32) - 1;
   double cA[CH], cB[CH];
   auto fetch = [&](double (&col)[CH], int j) {  // rows i < j of column j
-    const double* src = Rg + hoff(max(j, 0));
+    const double* src = Rg + hpk(max(j, 0));
 #pragma unroll
     for (int q = 0; q <= S0; ++q) {
       const int i = lane + 32 * q;
@@ -1105,7 +1223,7 @@ __device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double be
 #pragma unroll
   for (int s = 0; s < CH; ++s) {
     const int j = lane + 32 * s;
-    colp[s] = c.Rg + hoff(j);
+    colp[s] = c.Rg + hpk(j);
     top[s] = j < width ? hld(colp[s]) : 0.0;
   }
   double gcur = beta;
@@ -1186,7 +1304,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
     basis_store<EL>(c, k, w);
     const double nv = -(dsum * rnrm);
     {  // Hessenberg column k-1 (rows 0..k) to the packed matrix in L2
-      double* hc = c.Rg + hoff(k - 1);
+      double* hc = c.Rg + hpk(k - 1);
 #pragma unroll
       for (int s = 0; s < CHK; ++s) {
         const int i = lane + 32 * s;
@@ -1333,7 +1451,8 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   c.g = w; w += d.N2 + 2;
 #endif
   c.Vs = reinterpret_cast<double2*>(w); w += (size_t)a.ks * 2 * 32 * EL;
-  double* hs = w; w += a.h_smem_doubles;
+  double* hs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w) + 31) & ~(uintptr_t)31);  // 32-byte aligned columns (hpk)
+  w += a.h_smem_doubles;
   *extra = w;
   const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
   c.Vg = reinterpret_cast<double2*>(a.Vws + slot * a.v_stride);
@@ -1342,7 +1461,10 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int EL, int M, int NC, bool STRICT>
+// FORCED: forced forward solves -- eval_forward!(...; forcing) with an explicit forcing array (a.forcing_in), or the P x ncol
+// forced solves of eval_grad_forced (a.base_history: item b is control parameter b, zero initial state, control vector 0,
+// the guard-penalty derivative accumulated on the way, no history written).
+template <int EL, int M, int NC, bool STRICT, bool FORCED = false>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
@@ -1366,18 +1488,42 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
     const int seg = (int)(ticket / items);
     const size_t item = ticket % items;
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
-    const double* cvb = a.cvals + (size_t)b * (d.nsteps + 1) * cv_stride;
-    double* hist = a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b);
+    const bool gradf = FORCED && a.base_history != nullptr;
+    const double* cvb = a.cvals + (gradf ? (size_t)0 : (size_t)b * (d.nsteps + 1) * cv_stride);
+    double* hist = a.history ? a.history + slot_sz * a.nslots * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
     double* carry = a.final_state + (size_t)N2 * ((size_t)cl + (size_t)d.ncol * b);  // state between segments; w_N at the end
     const int n0 = seg * S, n1 = min(n0 + S, d.nsteps);
     const bool last = seg == nseg - 1;
+    // forcing of time level n (FORCED kernels only)
+    const double* fin = (FORCED && a.forcing_in) ? a.forcing_in + (size_t)N2 * M * (d.nsteps + 1) * ((size_t)cl + (size_t)d.ncol * b) : nullptr;
+    const double* hb = gradf ? a.base_history + slot_sz * (d.nsteps + 1) * (size_t)cl : nullptr;
+    const size_t tab_stride = (size_t)2 * (M + 1) * d.P;
+    auto forcing_at = [&](int n) {
+      FastForcing F;
+      F.arr = fin ? fin + (size_t)N2 * M * n : nullptr;
+      F.hb = hb ? hb + slot_sz * n : nullptr;
+      F.tp = gradf ? d.table + tab_stride * n + b : nullptr;
+      F.tq = gradf ? F.tp + (size_t)(M + 1) * d.P : nullptr;
+      F.P = d.P; F.kop = gradf ? a.theta_op[b] - 1 : 0;  // theta_op holds blob indices: operator 0 is the drift
+      return F;
+    };
+    // eval_grad_forced: d/dtheta of the guard penalty, dt/tf sum_n wt_n (<dpsi_n, W psi_n> + <psi_n, W dpsi_n>) with the
+    // diagonal W of this kernel family = 2 wt_n sum_r W_rr dpsi_r psi_r (src/eval_grad_forced.jl:150-172); per-lane partial
+    double gpen = 0.0;
+    auto guard_cross = [&](const Vec<EL>& dx, int n) {
+      Vec<EL> w0;
+      vload_cg(w0, hb + slot_sz * n, N, lane);
+      const double wt = (n == 0 || n == d.nsteps) ? 1.0 : 2.0;
+#pragma unroll
+      for (int e = 0; e < EL; ++e) gpen = fma(wt * R.wu[e] * dx.u[e], w0.u[e], fma(wt * R.wv[e] * dx.v[e], w0.v[e], gpen));
+    };
     Vec<EL> x;
     if (seg == 0) {
 #pragma unroll
       for (int e = 0; e < EL; ++e) {
         const int r = lane + 32 * e;
-        x.u[e] = r < N ? d.u0[r + (size_t)N * col] : 0.0;
-        x.v[e] = r < N ? d.v0[r + (size_t)N * col] : 0.0;
+        x.u[e] = (r < N && !gradf) ? d.u0[r + (size_t)N * col] : 0.0;
+        x.v[e] = (r < N && !gradf) ? d.v0[r + (size_t)N * col] : 0.0;
       }
     } else {
       wait_segment(a.progress + item, seg, lane, a.err);
@@ -1387,15 +1533,39 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
     const int nend = last ? n1 : n1 - 1;  // the last segment also forms the Taylor columns at the final time (forward_evolution.jl:232-242)
     for (int n = n0; n <= nend; ++n) {
       Vec<EL> rhs, guess;
-      double* slot = (n % a.save_every == 0) ? hist + slot_sz * (n / a.save_every) : nullptr;
-      fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, rhs, a_tay, &guess, slot);      // explicit part at t_n
-      if (n == d.nsteps) break;
+      double* slot = (hist && n % a.save_every == 0) ? hist + slot_sz * (n / a.save_every) : nullptr;
+      if constexpr (FORCED) {
+        if (gradf) guard_cross(x, n);
+        if (n == d.nsteps) {  // Taylor columns at the final time, WITHOUT forcing as in the reference (forward_evolution.jl:232-242)
+          fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, rhs, a_tay, &guess, slot);
+          break;
+        }
+        const FastForcing F = forcing_at(n);
+        fwd_fast<EL, M, NC, true, true>(c, R, x, a_rhs, rhs, a_tay, &guess, slot, &F);  // explicit part at t_n
+      } else {
+        fwd_fast<EL, M, NC, true>(c, R, x, a_rhs, rhs, a_tay, &guess, slot);      // explicit part at t_n
+        if (n == d.nsteps) break;
+      }
       load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n + 1) * cv_stride);              // implicit part uses t_{n+1}
+      if constexpr (FORCED) {  // the forcing of t_{n+1} is explicit: its implicit-side combination moves to the right-hand side
+        const FastForcing F1 = forcing_at(n + 1);                                 // (forward_evolution.jl:196-206)
+        Vec<EL> zero, fh;
+        vzero(zero);
+        fwd_fast<EL, M, NC, false, true>(c, R, zero, a_lhs, fh, nullptr, nullptr, nullptr, &F1);
+        vaxpy(rhs, -1.0, fh);
+      }
       x = guess;
       const int it = gmres_fast<EL, NC, QGD_FWD_VARIANT, STRICT>(c, R, op, x, rhs, d.abstol, N2, N2);
       if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
     }
     vstore(x, carry, N, lane);
+    if constexpr (FORCED) {
+      if (gradf) {  // guard-penalty derivative partial of this segment; the sum is carried in guardcol across segments
+        const double g = warp_allsum(gpen) * (d.dt / d.tf);
+        double* gc = a.guardcol + ((size_t)cl + (size_t)d.ncol * b);
+        if (lane == 0) *gc = (seg == 0 ? 0.0 : __ldcg(gc)) + g;
+      }
+    }
     publish_segment(a.progress + item, seg, lane);
   }
   if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);

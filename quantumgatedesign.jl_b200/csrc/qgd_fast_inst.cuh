@@ -42,7 +42,7 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   // least squares reads shared memory instead of waiting an L2 round trip per rotation.
   L.h_smem = 0;
   {
-    const long hd = ((long)restart * (restart + 3) / 2 + 2 + 1) & ~1L;
+    const long hd = ((long)hpk(restart) + 8 + 3) & ~3L;  // packed Hessenberg matrix + alignment slack
     const long want_vec = std::max(restart + 1 - L.kt, 0);
     if (L.wpc <= 2 && restart >= 2 && per_warp - base - hd >= std::min<long>(want_vec, 16) * vec) L.h_smem = (int)hd;
   }
@@ -65,7 +65,7 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
 void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, SweepArgs& a) {
   const size_t warps = (size_t)L.grid * L.wpc;
   a.v_stride = (size_t)(std::max(restart + 1 - L.ks - L.kt, 1) + QGD_MGS_BLOCK) * 2 * 32 * el;
-  a.h_stride = (size_t)restart * (restart + 3) / 2 + 2;
+  a.h_stride = ((size_t)std::max(hpk(restart), restart * (restart + 3) / 2) + 8 + 3) & ~(size_t)3;  // 32-byte aligned slots
   const size_t v_bytes = (warps * a.v_stride * 8 + 255) & ~(size_t)255;
   h->d_V.reserve(v_bytes + warps * a.h_stride * 8);
   a.Vws = h->d_V.as<double>();
@@ -120,11 +120,11 @@ void launch_sweep(qgd_handle* h, void (*kernel)(KArgs...), const FastCfg& L, Arg
   h->stats.kernel_launches++;
 }
 
-template <int EL, int M, int NC, bool STRICT>
+template <int EL, int M, int NC, bool STRICT, bool FORCED = false>
 void launch_forward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
-  FastCfg L = plan_fast(h, k_forward_fast<EL, M, NC, STRICT>, fast_fixed_doubles<EL, M, NC, STRICT>(d.N2), EL, (size_t)a.B * d.ncol, 0, d.N2);
+  FastCfg L = plan_fast(h, k_forward_fast<EL, M, NC, STRICT, FORCED>, fast_fixed_doubles<EL, M, NC, STRICT>(d.N2), EL, (size_t)a.B * d.ncol, 0, d.N2);
   ensure_krylov_fast(h, L, EL, d.N2, a);
-  launch_sweep(h, k_forward_fast<EL, M, NC, STRICT>, L, d, a);
+  launch_sweep(h, k_forward_fast<EL, M, NC, STRICT, FORCED>, L, d, a);
 }
 template <int EL, int M, int NC, bool STRICT>
 void launch_backward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
@@ -150,6 +150,7 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
 #define QGD_FAST_CASE_FWD(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC, false>(h, d, a); return true; }
 #define QGD_FAST_CASE_BWD(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC, false>(h, d, a); return true; }
 #define QGD_FAST_CASE_FWD_S(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC, true>(h, d, a); return true; }
+#define QGD_FAST_CASE_FWD_F(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC, false, true>(h, d, a); return true; }
 #define QGD_FAST_CASE_BWD_S(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC, true>(h, d, a); return true; }
 #define QGD_FAST_CASE_DER(EL, M, NC) if (el == EL && nc == NC) { launch_derivs_fast_t<EL, M, NC>(h, d, a, uv, ncols, cv, adjoint); return true; }
 
@@ -172,4 +173,11 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
   }                                                                                                                         \
   bool launch_backward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                      \
     QGD_FAST_SHAPES(QGD_FAST_CASE_BWD_S, M) return false;                                                                   \
+  }
+
+// The forced forward solves (eval_forward! with forcing, eval_grad_forced) on the register-operator sweeps, in translation
+// units of their own.
+#define QGD_DEFINE_FAST_LAUNCHERS_FORCED(M)                                                                                 \
+  bool launch_forward_fast_forced_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                       \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_FWD_F, M) return false;                                                                   \
   }

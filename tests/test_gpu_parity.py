@@ -315,9 +315,14 @@ def test_forced_forward_vs_oracle(q, O, name):
     forcing = np.asfortranarray(forcing)
     h = q.Handle(prob, controls)
     out = h.eval_forward(pcof, order=order, forcing=forcing)
+    # sparse dispersive problems take the register-operator sweeps for forced solves too (round 2); the others the generic ones
+    assert h.stats()["fast_path_launches"] == (1 if name in ("cnot2", "cnot3_333") else 0)
     ref_hist, ref_it = O.eval_forward(prob, controls, pcof, order=order, forcing=forcing)
     assert rel(out["history"][..., 0], ref_hist) < RTOL
-    assert np.array_equal(out["iters"][:, :, 0], ref_it)
+    if name in ("cnot2", "cnot3_333"):  # blocked orthogonalisation: a count may differ by one where the estimate grazes the tolerance
+        assert np.abs(out["iters"][:, :, 0] - ref_it).max() <= 1 and np.mean(out["iters"][:, :, 0] != ref_it) <= 0.01
+    else:
+        assert np.array_equal(out["iters"][:, :, 0], ref_it)
     # the forcing really enters (the unforced history differs)
     plain = h.eval_forward(pcof, order=order)
     assert rel(plain["history"][..., 0], ref_hist) > 1e-6
@@ -331,6 +336,9 @@ def test_eval_grad_forced_vs_oracle_and_adjoint(q, O, name):
     exactness check (test/GradientTests/compare_gradients.jl:47-66)."""
     prob, controls, pcof, target, order = _cases(q)[name]
     gf = q.eval_grad_forced(prob, controls, pcof, target, order=order)
+    st = q.get_handle(prob, controls).stats()
+    # the P x nic forced solves of a sparse dispersive problem run on the register-operator sweeps (round 2)
+    assert st["fast_path_launches"] == (2 if name in ("cnot2", "cnot3_333", "rabi_carrier") else 0), st
     ref = O.eval_grad_forced(prob, controls, pcof, target, order=order)
     assert rel(gf, ref) < RTOL
     ga = q.discrete_adjoint(prob, controls, pcof, target, order=order)

@@ -308,3 +308,22 @@ def test_c_program_drives_the_abi(q):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0 and "OK" in r.stdout
+
+
+# ---- LU preconditioner beyond the small sizes of round 1 -------------------------------------------------------------
+@pytest.mark.parametrize("N,nic,order", [(128, 5, 8), (100, 3, 6)])
+def test_lu_preconditioner_larger_sizes(q, O, N, nic, order):
+    """LUPreconditioner (src/preconditioners.jl:44-55: lu(LHS) then ldiv!) is applied here as the explicit inverse formed once
+    per sweep (Gauss-Jordan with partial pivoting).  N = 128 runs on the tensor-core sweeps (inverse applied per column),
+    N = 100 (not a multiple of 32) on the generic kernels: histories and iteration counts against the oracle, which factors
+    and substitutes like the reference."""
+    prob, controls, pcof, target, _ = q.configs.dense_random(N=N, nic=nic, Nc=2, nsteps=4, order=order, gmres_tol=1e-13, dt_norm=0.7,
+                                                             preconditioner_type=q.LUPreconditioner)
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_history=True, want_iters=True)
+    h.close()
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert rel(out["history"][..., 0], ref["history"]) < RTOL
+    assert np.abs(out["iters_fwd"][:, :, 0] - ref["iters_fwd"]).max() <= 1 and np.abs(out["iters_adj"][:, :, 0] - ref["iters_adj"]).max() <= 1
+    assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
