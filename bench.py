@@ -514,7 +514,8 @@ def run_b200(args):
         extra = extras_single_gpu(q, h, args, prob, controls, tgt, target, order, P, local)
         h.close()
         try:
-            extra["c4"] = c4_measure(q, torch, None, 0, 1, local, nsteps=1000, B=4, steps=1, warmup=1, with_cpu=not args.no_cpu_baseline)
+            # 9 control vectors = 288 column groups = 1.95 waves of 148 CTAs (4 would leave 20 SMs idle)
+            extra["c4"] = c4_measure(q, torch, None, 0, 1, local, nsteps=1000, B=9, steps=1, warmup=1, with_cpu=not args.no_cpu_baseline)
         except Exception as e:  # noqa: BLE001
             extra["c4"] = {"error": f"{type(e).__name__}: {e}"}
         line["extra"] = extra

@@ -262,6 +262,28 @@ def test_communicator_of_one_rank_matches_plain_handle(q):
         h.close()
 
 
+def test_multi_gpu_set_of_one_device(q):
+    """qgd_init_multi_gpu with ONE device (no communicator is created): the single-process entry points on the box the driver
+    tests on; both sharding modes must reproduce the plain handle bit for bit."""
+    prob, controls, pcof, target, order = q.configs.cnot2(nsteps=12, tf=12.0, gmres_tol=1e-13)
+    tgt = q.complex_to_real(target)
+    pcs = np.stack([pcof, 0.7 * pcof], axis=1)
+    plain = q.Handle(prob, controls)
+    ref = plain.discrete_adjoint(pcs, tgt, order=order)
+    plain.close()
+    mg = q.backend.MultiGPU(prob, controls, 1)
+    for shard in (q.backend.SHARD_COLUMNS, q.backend.SHARD_CONTROL_VECTORS):
+        out = mg.discrete_adjoint(pcs, tgt, order=order, shard=shard)
+        assert np.array_equal(out["grad"], ref["grad"]) and np.array_equal(out["infidelity"], ref["infidelity"])
+        assert np.array_equal(out["guard_penalty"], ref["guard_penalty"])
+    mg.set_nsteps(6)
+    mg.set_gmres_tolerances(1e-12, 1e-12)
+    assert np.isfinite(mg.discrete_adjoint(pcs, tgt, order=order)["grad"]).all()
+    mg.close()
+    with pytest.raises(q.QGDError):
+        q.backend.MultiGPU(prob, controls, 64)  # more GPUs than the box has
+
+
 def _ngpu():
     try:
         import torch
