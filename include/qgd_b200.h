@@ -162,6 +162,14 @@ int qgd_eval_forward(qgd_handle_t *h, const double *pcof, int64_t n_batch, int32
                      int64_t save_every, double *history, double *final_state,
                      int64_t *gmres_iters);
 
+/* The same split in two, so that several handles (each owns a stream) run their sweeps CONCURRENTLY on one GPU: the
+ * step-size studies of the reference (get_histories, src/Tests/test_convergence.jl:76-121; estimate_timesteps_per_period,
+ * src/calculate_timestep.jl:58-98) solve the same problem at nsteps = base * 2^k, k = 0..5 -- six launches of 8 warps each,
+ * which fill a B200 only when they overlap.  _async uploads pcof and enqueues; _collect synchronises and copies out. */
+int qgd_eval_forward_async(qgd_handle_t *h, const double *pcof, int64_t n_batch, int32_t order,
+                           int64_t save_every, int32_t want_iters);
+int qgd_eval_forward_collect(qgd_handle_t *h, double *history, double *final_state, int64_t *gmres_iters);
+
 /* eval_forward! with the `forcing` keyword (src/forward_evolution.jl:33-37, 118-129, 167-206): the forcing enters the
  * Taylor recursion at t_n (compute_derivatives!(...; forcing_matrix), src/hermite.jl:91-95) and, being explicit, the
  * implicit-side combination of the forcing at t_{n+1} is moved to the right-hand side; the Taylor columns stored for

@@ -29,7 +29,7 @@ EXPORTS = [
     "qgd_set_option", "qgd_get_option", "qgd_synchronize", "qgd_comm_set_nccl_library", "qgd_comm_get_unique_id",
     "qgd_comm_init_rank", "qgd_comm_finalize", "qgd_init_multi_gpu", "qgd_multi_n_gpus", "qgd_multi_handle",
     "qgd_multi_set_nsteps", "qgd_multi_set_gmres_tolerances", "qgd_multi_discrete_adjoint", "qgd_multi_destroy",
-    "qgd_measure_dmma_peak",
+    "qgd_measure_dmma_peak", "qgd_eval_forward_async", "qgd_eval_forward_collect",
 ]
 
 # option keys of qgd_set_option (include/qgd_b200.h)
@@ -92,6 +92,8 @@ def lib():
                                               c_double_p, c_int64_p]
         L.qgd_discrete_adjoint_tables.argtypes = [C.c_void_p, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
                                                   c_double_p, c_double_p, c_double_p]
+        L.qgd_eval_forward_async.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32]
+        L.qgd_eval_forward_collect.argtypes = [C.c_void_p, c_double_p, c_double_p, c_int64_p]
         L.qgd_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
         L.qgd_get_option.argtypes = [C.c_void_p, C.c_int32, c_int64_p]
         L.qgd_synchronize.argtypes = [C.c_void_p, C.c_void_p]
@@ -229,6 +231,23 @@ class Handle:
             f = np.asfortranarray(f)
             _check(lib().qgd_eval_forward_forced(self._h, _dp(pc), B, int(order), int(save_every), _dp(f), _dp(hist),
                                                  _dp(final), _ip(iters)))
+        return dict(history=hist, final_state=final, iters=iters)
+
+    def eval_forward_async(self, pcof, order=2, save_every=1, want_iters=False):
+        """Enqueue a forward solve on this handle's stream and return at once (qgd_eval_forward_async); several handles
+        overlap on the GPU.  Finish with `eval_forward_collect`."""
+        pc = self._pcof(pcof, self.P)
+        self._pending = (pc.shape[1], int(order), int(save_every), bool(want_iters))
+        _check(lib().qgd_eval_forward_async(self._h, _dp(pc), pc.shape[1], int(order), int(save_every), int(bool(want_iters))))
+
+    def eval_forward_collect(self, want_history=True):
+        B, order, save_every, want_iters = self._pending
+        m = order // 2
+        nslots = 1 + self.nsteps // save_every
+        hist = np.zeros((self.N2, 1 + m, nslots, self.ncol, B), order="F") if want_history else None
+        final = np.zeros((self.N2, self.ncol, B), order="F")
+        iters = np.zeros((self.nsteps, self.ncol, B), dtype=np.int64, order="F") if want_iters else None
+        _check(lib().qgd_eval_forward_collect(self._h, _dp(hist), _dp(final), _ip(iters)))
         return dict(history=hist, final_state=final, iters=iters)
 
     # -- host-evaluated controls (QGD_CONTROL_HOST_TABLE): tables instead of pcof
@@ -475,3 +494,6 @@ def clear_handles():
     for h in _HANDLES.values():
         h.close()
     _HANDLES.clear()
+    from . import convergence  # the per-level handles of get_histories
+
+    convergence.clear_level_pool()

@@ -5,8 +5,11 @@
     estimate_N_timesteps            src/calculate_timestep.jl (frequency estimate of the drift + max-amplitude controls)
     estimate_timesteps_per_period   src/calculate_timestep.jl:58-98
 
-Host orchestration only: every forward solve is `eval_forward` on the device (one handle, `nsteps` changed in place
-as the reference mutates `prob.nsteps`); the JLD2 logging of the reference is replaced by the returned dict.
+Host orchestration only: every forward solve is `eval_forward` on the device; the JLD2 logging of the reference is replaced
+by the returned dict.  The refinement levels of one order are independent solves of 8 warps each, so they are ENQUEUED TOGETHER
+-- one handle (= one stream) per level through `qgd_eval_forward_async`, collected afterwards -- and overlap on the GPU: the
+sweep of an order costs the time of its finest level instead of the sum over the levels (`concurrent=False` restores the
+reference's one-after-the-other loop; host-evaluated controls always take it).
 """
 from __future__ import annotations
 
@@ -16,7 +19,9 @@ from collections import OrderedDict
 import numpy as np
 
 from .api import eval_forward
-from .controls import GRAPEControl
+from .backend import Handle, problem_key
+from .controls import GRAPEControl, has_host_controls
+from .problem import real_to_complex
 
 
 def richardson_extrap_sol(Ah, A2h, order):
@@ -31,23 +36,64 @@ def richardson_extrap_rel_err(Ah, A2h, order):
     return float(np.linalg.norm(sol - Ah) / np.linalg.norm(sol))
 
 
+# One handle (= one stream + its device buffers) per refinement level, kept for the next call on the same problem: creating a
+# handle costs ~0.1 s (allocations, preconditioner factors, control table), far more than a level's sweep.
+_LEVEL_POOL = {"key": None, "handles": []}
+
+
+def clear_level_pool():
+    for h in _LEVEL_POOL["handles"]:
+        h.close()
+    _LEVEL_POOL["key"], _LEVEL_POOL["handles"] = None, []
+
+
+def _forward_levels_concurrent(prob, controls, pcof, order, levels, device):
+    """levels: [(nsteps, save_every)] -> [(complex history [N, 1+nsteps/save, nic], device seconds)], all levels in flight at once."""
+    key = (problem_key(prob, controls), device)
+    if _LEVEL_POOL["key"] != key:
+        clear_level_pool()
+        _LEVEL_POOL["key"] = key
+    pool = _LEVEL_POOL["handles"]
+    while len(pool) < len(levels):
+        pool.append(Handle(prob, controls, device))
+    for h, (nsteps, save) in zip(pool, levels):
+        h.set_nsteps(nsteps)
+        h.set_gmres_tolerances(prob.gmres_abstol, prob.gmres_reltol)
+        h.eval_forward_async(pcof, order=order, save_every=save)
+    out = []
+    for h, _ in zip(pool, levels):
+        r = h.eval_forward_collect()
+        out.append((real_to_complex(r["history"][:, 0, :, :, 0]), h.stats()["last_forward_ms"] * 1e-3))
+    return out
+
+
 def get_histories(prob, controls, pcof, N_iterations, orders=(2, 4, 6, 8, 10), min_error_limit=-np.inf,
-                  max_error_limit=-np.inf, base_nsteps=None, nsteps_change_factor=2, start_iteration=1, device=-1):
+                  max_error_limit=-np.inf, base_nsteps=None, nsteps_change_factor=2, start_iteration=1, device=-1,
+                  concurrent=True):
     """test_convergence.jl:20-146: for every order, N_iterations forward solves with nsteps = base * factor^(k-1) and
     saveEveryNsteps = factor^(k-1) (so all histories share the base time grid), Richardson error between consecutive
     refinements, early exit on precision reached / numerical saturation.  Returns the reference's dict of dicts."""
     p = prob.copy()
     base = prob.nsteps if base_nsteps is None else int(base_nsteps)
     ret = OrderedDict()
+    concurrent = concurrent and not has_host_controls(controls)
     for order in orders:
         summary = dict(order=order, nsteps=[], step_sizes=[], elapsed_times=[], histories=[], richardson_errors=[])
         ret[f"Order {order} (QGD)"] = summary
-        for k in range(start_iteration, N_iterations + 1):
+        ks = list(range(start_iteration, N_iterations + 1))
+        pre = None
+        if concurrent:  # every level of this order in flight at once; the stopping rules below only truncate what is returned
+            pre = _forward_levels_concurrent(prob, controls, pcof, order,
+                                             [(base * nsteps_change_factor ** (k - 1), nsteps_change_factor ** (k - 1)) for k in ks], device)
+        for idx, k in enumerate(ks):
             mult = nsteps_change_factor ** (k - 1)
             p.nsteps = base * mult
-            t0 = time.perf_counter()
-            history = eval_forward(p, controls, pcof, order=order, saveEveryNsteps=mult, device=device)
-            elapsed = time.perf_counter() - t0
+            if pre is not None:
+                history, elapsed = pre[idx]
+            else:
+                t0 = time.perf_counter()
+                history = eval_forward(p, controls, pcof, order=order, saveEveryNsteps=mult, device=device)
+                elapsed = time.perf_counter() - t0
             err = float("nan")
             if summary["histories"]:
                 err = richardson_extrap_rel_err(history, summary["histories"][-1], order)

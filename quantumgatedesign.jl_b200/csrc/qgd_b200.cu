@@ -828,6 +828,38 @@ int qgd_eval_forward(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32
   });
 }
 
+int qgd_eval_forward_async(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32_t order, int64_t save_every, int32_t want_iters) {
+  return guarded([&]() {
+    require(h && pcof && n_batch >= 1, "bad arguments");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    reset_stats(h);
+    const int B = (int)n_batch;
+    h->pend_B = 0;
+    h->d_pcof.reserve((size_t)std::max(h->P, 1) * B * 8);
+    h2d(h, h->d_pcof.p, pcof, (size_t)h->P * B * 8);  // pageable source: staged before the call returns
+    run_forward(h, h->d_pcof.as<double>(), B, order, save_every, want_iters != 0);
+    remember_hist_pcof(h, pcof, B);
+    h->pend_B = B; h->pend_order = order; h->pend_save = save_every; h->pend_iters = want_iters;
+  });
+}
+int qgd_eval_forward_collect(qgd_handle_t* h, double* history, double* final_state, int64_t* gmres_iters) {
+  return guarded([&]() {
+    require(h != nullptr, "null handle");
+    if (h->pend_B < 1) throw QgdError(QGD_ESTATE, "qgd_eval_forward_collect without a pending qgd_eval_forward_async");
+    if (gmres_iters && !h->pend_iters) throw QgdError(QGD_EINVAL, "iteration counts were not requested from qgd_eval_forward_async");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const int B = h->pend_B, m = h->pend_order / 2;
+    const int nslots = 1 + (int)(h->nsteps / h->pend_save);
+    h->pend_B = 0;
+    if (history) d2h(h, history, h->d_history.p, (size_t)h->N2 * (m + 1) * nslots * h->ncol * B * 8);
+    if (final_state) d2h(h, final_state, h->d_final.p, (size_t)h->N2 * h->ncol * B * 8);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    check_device_error(h);
+    iters_out(h, gmres_iters, h->d_iters_f, (size_t)h->nsteps * h->ncol * B);
+    finish_timing(h, true, false);
+  });
+}
+
 int qgd_eval_forward_forced(qgd_handle_t* h, const double* pcof, int64_t n_batch, int32_t order, int64_t save_every,
                             const double* forcing, double* history, double* final_state, int64_t* gmres_iters) {
   return guarded([&]() {

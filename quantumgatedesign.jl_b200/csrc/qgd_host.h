@@ -72,6 +72,8 @@ struct qgd_handle {
   int64_t hist_nsteps = 0, hist_save = 0;
   bool hist_valid = false;
   int phase_B = 0, phase_order = 0;  // two-phase API
+  int pend_B = 0, pend_order = 0, pend_iters = 0;  // qgd_eval_forward_async waiting for its _collect
+  int64_t pend_save = 0;
   // register-operator fast path (qgd_fast.cuh): structure test done once at creation
   bool fast_ok = false;
   int fast_el = 0;

@@ -57,14 +57,32 @@ __device__ __forceinline__ void vscale(Vec<EL>& y, double a) {
 #pragma unroll
   for (int e = 0; e < EL; ++e) { y.u[e] *= a; y.v[e] *= a; }
 }
+// Sum of one double per lane, result in every lane, by two FP64 tensor-core DMMA.8x8x4 with a ones operand (measured 75
+// vs 175 cycles for the 5-stage shuffle butterfly, profiles/r01_microbench.txt): B operand (4x8, lane l <-> B[l%4][l/4]) = p,
+// A = ones: D[i][j] = sum of the 4 lanes of group j, lane l receives groups 2(l%4), 2(l%4)+1; their sum as A operand
+// (8x4, lane l <-> A[l/4][l%4]) times ones gives the total in every lane.
+__device__ __forceinline__ double warp_sum_dmma(double p) {
+  double c0, c1, t0, t1;
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(c0), "=d"(c1) : "d"(1.0), "d"(p), "d"(0.0), "d"(0.0));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(t0), "=d"(t1) : "d"(c0 + c1), "d"(1.0), "d"(0.0), "d"(0.0));
+  return t0;
+}
+#ifndef QGD_GENERIC_DMMA_RED
+#define QGD_GENERIC_DMMA_RED 1  // 1: the dot products of the generic sweeps reduce with warp_sum_dmma instead of the shuffle butterfly
+#endif
+
 template <int EL>
-__device__ __forceinline__ double vdot(const Vec<EL>& a, const Vec<EL>& b) {  // warp-shuffle batched dot
+__device__ __forceinline__ double vdot(const Vec<EL>& a, const Vec<EL>& b) {  // warp-level batched dot
   double s = 0.0;
 #pragma unroll
   for (int e = 0; e < EL; ++e) s = fma(a.u[e], b.u[e], s);
 #pragma unroll
   for (int e = 0; e < EL; ++e) s = fma(a.v[e], b.v[e], s);
+#if QGD_GENERIC_DMMA_RED
+  return warp_sum_dmma(s);
+#else
   return warp_sum(s);
+#endif
 }
 
 // Per-warp context: everything lane-invariant.
@@ -385,6 +403,9 @@ __device__ inline void solve_least_squares(const WarpCtx& c, int width, double b
   }
 }
 
+#ifndef QGD_GENERIC_PREFETCH
+#define QGD_GENERIC_PREFETCH 1  // Krylov basis vectors of the generic sweeps prefetched two ahead (0: one L2 round trip per vector)
+#endif
 // GMRES (IterativeSolvers.jl gmres_iterable! / iterate).  OP::apply(ctx, in, out).
 // reltol < 0: fixed tolerance `abstol` (the time-stepping solves: update_gmres_iterable! never
 // refreshes the tolerance); else tol = max(reltol*beta0, abstol) (gmres! driver).
@@ -411,6 +432,7 @@ __device__ int gmres_warp(const WarpCtx& c, const OP& op, Vec<EL>& x, const Vec<
     op.apply(c, v, w);  // expand!
     precond_apply(c, w, pdir);
     double dsum = 0.0;
+#if !QGD_GENERIC_PREFETCH
     for (int i = 0; i < k; ++i) {  // modified Gram-Schmidt, one warp-shuffle dot per basis vector
       Vec<EL> vi;
       vload(vi, c.Vg + (size_t)i * N2, N, lane);
@@ -419,6 +441,23 @@ __device__ int gmres_warp(const WarpCtx& c, const OP& op, Vec<EL>& x, const Vec<
       vaxpy(w, -h, vi);
       dsum += c.nullv[i] * h;
     }
+#else
+    {  // modified Gram-Schmidt, one warp-shuffle dot per basis vector (strict: same operations in the same order as the
+       // reference).  The basis lives in L2: vectors i+1 and i+2 are in flight while vector i is being reduced, so the
+       // chain per vector is the reduction, not an L2 round trip (round 2: the generic sweeps were bound by exactly that).
+      Vec<EL> vi, vn, vnn;
+      vload(vi, c.Vg, N, lane);
+      vload(vn, c.Vg + (size_t)min(1, k - 1) * N2, N, lane);
+      for (int i = 0; i < k; ++i) {
+        vload(vnn, c.Vg + (size_t)min(i + 2, k - 1) * N2, N, lane);
+        const double h = vdot(vi, w);
+        if (lane == 0) c.hcol[i] = h;
+        vaxpy(w, -h, vi);
+        dsum += c.nullv[i] * h;
+        vi = vn; vn = vnn;
+      }
+    }
+#endif
     const double nrm = sqrt(vdot(w, w));
     vscale(w, 1.0 / nrm);
     vstore(w, c.Vg + (size_t)k * N2, N, lane);
@@ -438,10 +477,15 @@ __device__ int gmres_warp(const WarpCtx& c, const OP& op, Vec<EL>& x, const Vec<
       const int width = k - 1;
       __syncwarp();
       solve_least_squares(c, width, beta);
-      for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 1:k-1] y
-        Vec<EL> vj;
-        vload(vj, c.Vg + (size_t)j * N2, N, lane);
-        vaxpy(x, c.yv[j], vj);
+      {  // update_solution!: x += V[:, 1:k-1] y, two basis vectors in flight
+        Vec<EL> vj, vn, vnn;
+        vload(vj, c.Vg, N, lane);
+        vload(vn, c.Vg + (size_t)min(1, width - 1) * N2, N, lane);
+        for (int j = 0; j < width; ++j) {
+          vload(vnn, c.Vg + (size_t)min(j + 2, width - 1) * N2, N, lane);
+          vaxpy(x, c.yv[j], vj);
+          vj = vn; vn = vnn;
+        }
       }
       k = 1;
       if (cur > tol) {  // restart (residual.current keeps its value, as in the package)

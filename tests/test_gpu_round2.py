@@ -349,3 +349,29 @@ def test_lu_preconditioner_larger_sizes(q, O, N, nic, order):
     assert np.abs(out["iters_fwd"][:, :, 0] - ref["iters_fwd"]).max() <= 1 and np.abs(out["iters_adj"][:, :, 0] - ref["iters_adj"]).max() <= 1
     assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
     assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+
+
+# ---- get_histories: the refinement levels of an order enqueued together ----------------------------------------------
+def test_get_histories_concurrent_levels_equal_sequential(q):
+    """get_histories (src/Tests/test_convergence.jl:76-121): with `concurrent=True` every level of an order runs on its own
+    handle / stream through qgd_eval_forward_async and they overlap on the GPU; the histories must be bit for bit the ones of
+    the reference's one-after-the-other loop, and the async pair must refuse misuse."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=10, tf=10.0, gmres_tol=1e-13, subsystem_sizes=(3, 3, 3), D1=5)
+    seq = q.get_histories(prob, controls, pcof, 4, orders=(4, 8), concurrent=False)
+    con = q.get_histories(prob, controls, pcof, 4, orders=(4, 8), concurrent=True)
+    for key in seq:
+        assert seq[key]["nsteps"] == con[key]["nsteps"] == [10, 20, 40, 80]
+        for a, b in zip(seq[key]["histories"], con[key]["histories"]):
+            assert a.shape == b.shape == (27, 11, 8) and np.array_equal(a, b)
+        assert np.allclose(seq[key]["richardson_errors"][1:], con[key]["richardson_errors"][1:], rtol=0, atol=0)
+    h = q.Handle(prob, controls)
+    with pytest.raises(q.QGDError) as e:
+        h._pending = (1, order, 1, False)
+        h.eval_forward_collect()
+    assert e.value.code == -5  # collect without a pending async call
+    h.eval_forward_async(pcof, order=order, want_iters=True)
+    r = h.eval_forward_collect()
+    ref = h.eval_forward(pcof, order=order)
+    assert np.array_equal(r["history"], ref["history"]) and np.array_equal(r["iters"], ref["iters"])
+    h.close()
+    q.backend.clear_handles()
