@@ -999,6 +999,7 @@ int qgd_adjoint_phase1(qgd_handle_t* h, const double* pcof, int64_t n_batch, int
                        double* guard_local) {
   return guarded([&]() {
     require(h && pcof && n_batch >= 1, "bad arguments");
+    if (h->comm) throw QgdError(QGD_ESTATE, "this handle has a communicator: qgd_discrete_adjoint does both phases and the exchanges on the device");
     CUDA_CHECK(cudaSetDevice(h->device));
     reset_stats(h);
     const int B = (int)n_batch;
@@ -1026,6 +1027,7 @@ int qgd_adjoint_phase1(qgd_handle_t* h, const double* pcof, int64_t n_batch, int
 int qgd_adjoint_phase2(qgd_handle_t* h, const double* target, const double* final_state_all, double* grad_local, double* infidelity) {
   return guarded([&]() {
     require(h && target && final_state_all, "bad arguments");
+    if (h->comm) throw QgdError(QGD_ESTATE, "this handle has a communicator: qgd_discrete_adjoint does both phases and the exchanges on the device");
     if (!h->hist_valid || h->phase_B < 1) throw QgdError(QGD_ESTATE, "qgd_adjoint_phase2 without a preceding qgd_adjoint_phase1");
     CUDA_CHECK(cudaSetDevice(h->device));
     const int B = h->phase_B, order = h->phase_order;
