@@ -375,3 +375,69 @@ def test_get_histories_concurrent_levels_equal_sequential(q):
     assert np.array_equal(r["history"], ref["history"]) and np.array_equal(r["iters"], ref["iters"])
     h.close()
     q.backend.clear_handles()
+
+
+# ---- seeded random problems: shapes, orders, preconditioners and control families the named cases do not hit ----------
+def _random_case(q, seed):
+    """-> (prob, controls, pcof, target, order, description); seed-determined mix of dispersive (sparse) and dense problems."""
+    rng = np.random.default_rng(9000 + seed)
+    order = int(rng.choice([2, 4, 6, 8, 10, 12]))
+    nsteps = int(rng.integers(3, 9))
+    tf = float(nsteps) * float(rng.choice([0.5, 1.0]))
+    tol = float(rng.choice([1e-13, 1e-14]))
+    if seed % 2 == 0:  # dispersive, 1-3 subsystems with 2-4 levels each (register-operator sweeps when N <= 64)
+        nsub = int(rng.integers(1, 4))
+        sizes = tuple(int(rng.integers(2, 5)) for _ in range(nsub))
+        ess = tuple(int(rng.integers(1, s + 1)) for s in sizes)
+        freqs = 2 * np.pi * rng.uniform(3.5, 8.0, nsub)
+        kerr = 2 * np.pi * 0.2 * rng.random((nsub, nsub))
+        kerr = 0.5 * (kerr + kerr.T)
+        pre = [q.IdentityPreconditioner, q.DiagonalHamiltonianPreconditioner, q.LUPreconditioner][int(rng.integers(0, 3))]
+        prob = q.DispersiveProblem(sizes, ess, freqs, freqs, kerr, tf, nsteps, sparse_rep=bool(rng.integers(0, 2)),
+                                   gmres_abstol=tol, gmres_reltol=tol, preconditioner_type=pre)
+        desc = f"dispersive {sizes}/{ess} precond {pre}"
+    else:  # dense random operators (generic kernels; N = 32 / 64 the tensor-core sweeps)
+        N = int(rng.choice([3, 5, 9, 17, 32, 33, 64]))
+        nic = int(rng.integers(1, min(N, 6) + 1))
+        Nc = int(rng.integers(1, 4))
+        pre = [q.IdentityPreconditioner, q.DiagonalHamiltonianPreconditioner, q.LUPreconditioner][int(rng.integers(0, 3))]
+        prob, _, _, _, _ = q.configs.dense_random(N=N, nic=nic, Nc=Nc, nsteps=nsteps, order=order, gmres_tol=tol, dt_norm=0.4,
+                                                  preconditioner_type=pre, seed=100 + seed)
+        desc = f"dense N={N} nic={nic} Nc={Nc} precond {pre}"
+    controls = []
+    for k in range(prob.N_operators):
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            c = q.GRAPEControl(int(rng.integers(1, 6)), prob.tf)
+        elif kind == 1:
+            c = q.BSpline2Control(int(rng.integers(3, 9)), prob.tf)
+        elif kind == 2:
+            deg = int(rng.choice([2, 4, 8, 14]))
+            c = q.FortranBSplineControl(deg, deg + int(rng.integers(2, 8)), prob.tf)
+        else:
+            c = q.CarrierControl(q.BSpline2Control(int(rng.integers(3, 7)), prob.tf), list(rng.uniform(-3, 3, int(rng.integers(1, 4)))))
+        controls.append(c)
+    P = q.get_number_of_control_parameters(controls)
+    pcof = 0.1 * rng.standard_normal(P)
+    n, nic = prob.N_tot_levels, prob.N_initial_conditions
+    target = (rng.standard_normal((n, nic)) + 1j * rng.standard_normal((n, nic))) / np.sqrt(n)
+    return prob, controls, pcof, target, order, desc + f" order {order} nsteps {nsteps} controls {[type(c).__name__ for c in controls]}"
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_seeded_random_problems_vs_oracle(q, O, seed):
+    prob, controls, pcof, target, order, desc = _random_case(q, seed)
+    h = q.Handle(prob, controls)
+    h.set_option(q.backend.OPT_STRICT_MGS, 1)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_history=True, want_iters=True)
+    st = h.stats()
+    h.close()
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    print(desc, "| fast/dense sweeps:", st["fast_path_launches"], "| it/step", float(ref["iters_fwd"].mean()))
+    assert rel(out["history"][..., 0], ref["history"]) < RTOL, desc
+    assert rel(out["grad"][:, 0], ref["grad"]) < RTOL, desc
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * max(abs(ref["infidelity"]), 1e-12), desc
+    assert abs(out["guard_penalty"][0] - ref["guard_penalty"]) <= RTOL * max(abs(ref["guard_penalty"]), 1e-12), desc
+    df = np.abs(out["iters_fwd"][:, :, 0] - ref["iters_fwd"]).max()
+    da = np.abs(out["iters_adj"][:, :, 0] - ref["iters_adj"]).max()
+    assert df <= 1 and da <= 1, desc
