@@ -209,8 +209,9 @@ function eval_forward_b200!(uv_history::Array{Float64,4}, prob::SchrodingerProb,
     @assert size(uv_history) == (prob.real_system_size, 1 + m, 1 + div(prob.nsteps, saveEveryNsteps), prob.N_initial_conditions)
     h = b200_handle(prob, controls; device=device)
     GC.@preserve uv_history pcof forcing begin
-        if any(is_host_control, controls)
-            cvals, _ = control_tables(controls, pcof, prob.tf, prob.nsteps, m)
+        ctrl_list = controls isa AbstractControl ? [controls] : controls
+        if any(is_host_control, ctrl_list)
+            cvals, _ = control_tables(ctrl_list, pcof, prob.tf, prob.nsteps, m)
             qgd_check(ccall((:qgd_eval_forward_tables, libqgd), Cint,
                 (Ptr{Cvoid}, Int64, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
                 h.ptr, 1, order, saveEveryNsteps, cvals, uv_history, C_NULL, C_NULL))
