@@ -487,3 +487,53 @@ def test_two_warps_per_sm_launch_shape_equals_single_evaluations(q):
             assert np.array_equal(one["iters_fwd"][:, :, 0], batch["iters_fwd"][:, :, b])
             assert one["infidelity"][0] == batch["infidelity"][b]
     h.close()
+
+
+# ---- BASELINE configurations at their FULL size, through size-independent properties ---------------------------------------
+def test_c3_full_batch_of_1024_control_vectors_matches_single_evaluations(q):
+    """C3 (BASELINE.json configs[2]): 1024 random control vectors of the full-size C2 problem in ONE call; the elements picked
+    must equal the same control vector evaluated on its own, bit for bit (no cross-talk between the 8 192 columns in flight,
+    the ticket queue and the migration of columns between warps leave no trace in the numbers)."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=550, tf=550.0, gmres_tol=1e-12)
+    P = len(pcof)
+    pcs = np.asfortranarray(np.stack([q.configs.cnot3_pcof(P, s) for s in range(1024)], axis=1))
+    tgt = q.complex_to_real(target)
+    h = q.Handle(prob, controls)
+    batch = h.discrete_adjoint(pcs, tgt, order=order)
+    assert np.isfinite(batch["grad"]).all() and (batch["infidelity"] > 0).all() and (batch["infidelity"] < 1.0 + 1e-9).all()
+    for b in (0, 511, 1023):
+        one = h.discrete_adjoint(pcs[:, b], tgt, order=order)
+        assert np.array_equal(one["grad"][:, 0], batch["grad"][:, b])
+        assert one["infidelity"][0] == batch["infidelity"][b] and one["guard_penalty"][0] == batch["guard_penalty"][b]
+    h.close()
+
+
+def test_c4_full_size_norm_preservation_and_directional_derivative(q):
+    """C4 (BASELINE.json configs[3]) at its stated size: N = 256 dense, all 256 columns, 4 control operators, order 10, 1000 steps,
+    on the tensor-core sweeps.  The oracle cannot reach this size (a 16-column, 1-step evaluation takes minutes), so the check is
+    through properties that do not depend on it: (i) the Hermite step with a skew generator preserves the norm of every column
+    (to the GMRES tolerance accumulated over 1000 steps), (ii) the infidelity returned by the gradient call equals
+    infidelity_real of the final states of an independent forward call, (iii) the adjoint gradient reproduces the central
+    finite difference of the objective along a random direction (the reference's own check,
+    test/GradientTests/compare_gradients.jl:47-66, at the tolerance a fixed step allows)."""
+    prob, controls, pcof, target, order = q.configs.dense_random(N=256, nic=256, Nc=4, nsteps=1000, order=10, gmres_tol=1e-12,
+                                                                 dt_norm=1.0, n_basis=20, degree=8)
+    tgt = q.complex_to_real(target)
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, tgt, order=order)
+    assert h.stats()["fast_path_launches"] == 2
+    d = np.random.default_rng(11).standard_normal(len(pcof))
+    d /= np.linalg.norm(d)
+    eps = 1e-4
+    pcs = np.asfortranarray(np.stack([pcof, pcof + eps * d, pcof - eps * d], axis=1))
+    fwd = h.eval_forward(pcs, order=order, want_history=False, want_iters=False)
+    h.close()
+    psi = fwd["final_state"]                                   # [2N, nic, 3]
+    norms = np.sqrt((psi[:, :, 0] ** 2).sum(axis=0))
+    assert np.abs(norms - 1.0).max() < 1e-8, np.abs(norms - 1.0).max()
+    f = [q.infidelity_real(psi[:, :, b], tgt, prob.N_ess_levels) for b in range(3)]
+    assert abs(f[0] - out["infidelity"][0]) <= 1e-10 * abs(f[0])
+    fd = (f[1] - f[2]) / (2 * eps)                              # guard projector is zero for this problem: objective = infidelity
+    ad = float(out["grad"][:, 0] @ d)
+    print("C4 full size: infidelity", f[0], "directional derivative adjoint", ad, "central difference", fd, "max |norm - 1|", np.abs(norms - 1.0).max())
+    assert abs(fd - ad) <= 1e-6 * max(abs(ad), abs(fd)) + 1e-12
