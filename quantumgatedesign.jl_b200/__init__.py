@@ -19,5 +19,6 @@ from . import distributed
 from .api import (discrete_adjoint, discrete_adjoint_, discrete_adjoint_batch, eval_forward, eval_forward_,
                   eval_grad_forced, guard_penalty_real, infidelity, infidelity_real)
 from .backend import Handle, MultiGPU, QGDError, comm_unique_id, get_handle, measure_dmma_peak, measure_fp64_peak
+from .optimize import optimize_gate
 from .convergence import (estimate_N_timesteps, estimate_timesteps_per_period, get_histories, get_shortest_period,
                           richardson_extrap_rel_err, richardson_extrap_sol)

@@ -1006,6 +1006,7 @@ int qgd_adjoint_phase1(qgd_handle_t* h, const double* pcof, int64_t n_batch, int
     h->d_pcof.reserve((size_t)std::max(h->P, 1) * B * 8);
     h2d(h, h->d_pcof.p, pcof, (size_t)h->P * B * 8);
     run_forward(h, h->d_pcof.as<double>(), B, order, 1, false);
+    remember_hist_pcof(h, pcof, B);  // the history stays resident: a following qgd_discrete_adjoint(history_precomputed) may reuse it
     run_guard(h, B, order, false);
     h->d_guard.reserve((size_t)B * 8);
     h->d_grad.reserve((size_t)std::max(h->P, 1) * B * 8);

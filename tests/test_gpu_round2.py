@@ -537,3 +537,21 @@ def test_c4_full_size_norm_preservation_and_directional_derivative(q):
     ad = float(out["grad"][:, 0] @ d)
     print("C4 full size: infidelity", f[0], "directional derivative adjoint", ad, "central difference", fd, "max |norm - 1|", np.abs(norms - 1.0).max())
     assert abs(fd - ad) <= 1e-6 * max(abs(ad), abs(fd)) + 1e-12
+
+
+# ---- the production caller: optimize_gate's two closures on the device path --------------------------------------------
+def test_optimize_gate_reduces_objective_and_reuses_the_resident_history(q, O):
+    """optimize_gate (src/ipopt_optimal_control.jl:187-471; scipy L-BFGS-B in place of Ipopt): CNOT2 of examples/cnot2_optimization.jl
+    for a few iterations.  The objective must fall, every gradient asked for at the point just evaluated must have reused the
+    history left on the device by eval_f (history_precomputed), and the final objective terms must equal the oracle's at the
+    final control vector."""
+    prob, controls, pcof, target, order = q.configs.cnot2(nsteps=40, tf=100.0, gmres_tol=1e-12)
+    res = q.optimize_gate(prob, controls, pcof, target, order=order, maxIter=8, ridge_penalty_strength=1e-2)
+    print("optimize_gate: objective", res["initial_objective"], "->", res["final_objective"], "in", res["iterations"], "iterations,",
+          res["n_forward_solves"], "forward /", res["n_adjoint_solves"], "adjoint solves,", res["n_history_reused"], "histories reused")
+    assert res["final_objective"] < 0.5 * res["initial_objective"]
+    assert res["n_history_reused"] >= res["n_adjoint_solves"] - 1 and res["n_history_reused"] >= 3
+    ref = O.discrete_adjoint(prob, controls, res["final_pcof"], target, order=order)
+    assert abs(res["final_infidelity"] - ref["infidelity"]) <= 1e-9 * max(abs(ref["infidelity"]), 1e-3)
+    assert abs(res["final_guard_penalty"] - ref["guard_penalty"]) <= 1e-9 * max(abs(ref["guard_penalty"]), 1e-6)
+    q.backend.clear_handles()
