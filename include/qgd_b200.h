@@ -142,7 +142,10 @@ int qgd_set_gmres_tolerances(qgd_handle_t *h, double abstol, double reltol);
                                          * scalars dot(psi,R), dot(psi,T) per control vector, every rank solves its own
                                          * columns (the first one from a zero guess: lambda_N moves by the GMRES
                                          * tolerance; sparse problems only)                                             */
-#define QGD_OPT_MAX 10
+#define QGD_OPT_LATENCY_TEAM 11         /* the four-warps-per-column latency team of the register-operator sweeps: 0 (default)
+                                         * automatic -- taken when no more columns are in flight than the GPU has SMs, e.g.
+                                         * ONE gradient evaluation --, 1 always, 2 never                                 */
+#define QGD_OPT_MAX 11
 int qgd_set_option(qgd_handle_t *h, int32_t key, int64_t value);
 int qgd_get_option(qgd_handle_t *h, int32_t key, int64_t *value);
 

@@ -34,7 +34,7 @@ EXPORTS = [
 
 # option keys of qgd_set_option (include/qgd_b200.h)
 OPT_STRICT_MGS, OPT_DISABLE_FAST, OPT_DISABLE_DENSE_SWEEP, OPT_DISABLE_DENSE_DMMA, OPT_DENSE_TERMINAL = 1, 2, 3, 4, 5
-OPT_DISABLE_TMEM, OPT_SEG_STEPS, OPT_L2_PERSIST, OPT_LATENCY_WARPS, OPT_TERMINAL_EXCHANGE = 6, 7, 8, 9, 10
+OPT_DISABLE_TMEM, OPT_SEG_STEPS, OPT_L2_PERSIST, OPT_LATENCY_WARPS, OPT_TERMINAL_EXCHANGE, OPT_LATENCY_TEAM = 6, 7, 8, 9, 10, 11
 SHARD_COLUMNS, SHARD_CONTROL_VECTORS = 0, 1
 
 

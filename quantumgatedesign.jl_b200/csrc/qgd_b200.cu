@@ -560,13 +560,27 @@ bool try_forward_fast_forced(qgd_handle* h, const QgdDevProb& d, const SweepArgs
   if (!fast_applicable(h, d.m)) return false;
   QGD_FAST_SWITCH(d.m, launch_forward_fast_forced, h, d, a, h->fast_el, h->Nc)
 }
+bool try_forward_fast_team(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_forward_fast_team, h, d, a, h->fast_el, h->Nc)
+}
+bool try_backward_fast_team(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_backward_fast_team, h, d, a, h->fast_el, h->Nc)
+}
+// The latency team (four warps per column) pays when no more columns are in flight than the GPU has SMs
+bool team_wanted(const qgd_handle* h, const SweepArgs& a) {
+  if (h->opt[QGD_OPT_STRICT_MGS] || h->opt[QGD_OPT_LATENCY_TEAM] == 2) return false;
+  if (h->opt[QGD_OPT_LATENCY_TEAM] == 1) return true;
+  return (size_t)a.B * h->ncol <= (size_t)h->prop.multiProcessorCount;
+}
 // QGD_OPT_STRICT_MGS selects the strict modified Gram-Schmidt instantiation of the same sweeps
 bool try_forward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (!fast_applicable(h, d.m)) return false;
+  if (team_wanted(h, a) && try_forward_fast_team(h, d, a)) return true;
   return h->opt[QGD_OPT_STRICT_MGS] ? try_forward_fast_strict(h, d, a) : try_forward_fast_default(h, d, a);
 }
 bool try_backward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (!fast_applicable(h, d.m)) return false;
+  if (team_wanted(h, a) && try_backward_fast_team(h, d, a)) return true;
   return h->opt[QGD_OPT_STRICT_MGS] ? try_backward_fast_strict(h, d, a) : try_backward_fast_default(h, d, a);
 }
 bool try_derivs_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a, double* uv, int ncols, const double* cv, int adjoint) {
@@ -789,6 +803,7 @@ int qgd_set_option(qgd_handle_t* h, int32_t key, int64_t value) {
       case QGD_OPT_SEG_STEPS: require(value >= 0 && value <= (1 << 30), "QGD_OPT_SEG_STEPS must be >= 0"); break;
       case QGD_OPT_LATENCY_WARPS: require(value >= 0 && value <= QGD_WARPS_PER_CTA, "QGD_OPT_LATENCY_WARPS must be 0..8"); break;
       case QGD_OPT_TERMINAL_EXCHANGE: require(value == 0 || value == 1, "QGD_OPT_TERMINAL_EXCHANGE must be 0 or 1"); break;
+      case QGD_OPT_LATENCY_TEAM: require(value >= 0 && value <= 2, "QGD_OPT_LATENCY_TEAM must be 0, 1 or 2"); break;
       default: throw QgdError(QGD_EINVAL, "unknown option key " + std::to_string(key));
     }
     if (h->opt[key] != value) { h->opt[key] = value; h->hist_valid = false; }

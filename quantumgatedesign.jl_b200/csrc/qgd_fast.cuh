@@ -179,6 +179,7 @@ struct FastCtx {
   double2* Vs;    // smem [KS][32*EL]  Krylov basis, shared-memory tier
   double2* Vg;    // global            Krylov basis, tail (vector i >= KT+KS at (i-KT-KS)*32*EL)
   double* Rg;     // global            packed upper-triangular R: column j at j(j+1)/2
+  double* team;   // smem: shared state of the latency team (TeamView), null in the one-warp-per-column kernels
 };
 template <int EL, int M, int NC, bool STRICT = false>
 __host__ __device__ constexpr int fast_fixed_doubles(int N2) {
@@ -676,7 +677,9 @@ __device__ int gmres_fast_strict(const FastCtx<EL>& c, const RegOps<EL, NC>& R, 
       }
     }
     const double nrm2 = warp_allsum(vdot_local<EL>(w, w));
-    const double rnrm = rsqrt(nrm2), nrm = nrm2 * rnrm;  // 1/||w|| and ||w|| from one reciprocal square root
+    // 1/||w|| and ||w|| from one reciprocal square root; an exactly vanishing w (the Krylov space is exhausted: happy
+    // breakdown) gives H[k+1][k] = 0 as in the reference (its estimate then drops to zero and the solve ends), not 0 * inf
+    const double rnrm = rsqrt(nrm2), nrm = nrm2 > 0.0 ? nrm2 * rnrm : 0.0;
     vscale(w, rnrm);
     basis_store<EL>(c, k, w);
     {  // new rotation (k-1) from (hprev, nrm); update the rotated right-hand side
@@ -966,6 +969,175 @@ __device__ __forceinline__ void gs_orthogonalize_super(const FastCtx<EL>& c, int
   }
 }
 
+// ========================================================================================================
+// Latency team (round 2): ONE column on FOUR warps of an otherwise empty SM
+// ========================================================================================================
+// When no more columns are in flight than the GPU has SMs (a single gradient evaluation, what optimize_gate asks for:
+// src/ipopt_optimal_control.jl:257,304) a warp is alone on its SM and its GMRES iteration is one long dependent chain,
+// 45 % of it the orthogonalisation (profiles/r02_ncu_fwd_b1.txt).  The team spreads that part: the Krylov basis is dealt
+// out in blocks of 8 vectors to the four warps of the CTA -- block b lives in the tensor memory of warp b % 4 (each warp
+// owns a 32-lane quarter: 64 vectors each, the whole basis on chip) -- and a Gram-Schmidt step takes the coefficients of
+// FOUR blocks (one per warp) from the same vector: every warp loads its block, forms its 8 dot products and reductions and
+// its part of the update  sum_q h_q v_q, the parts are exchanged through shared memory and everybody applies all four.
+// Classical Gram-Schmidt inside a super-block of 32, modified across super-blocks (tools/gs_block_experiment.py: block
+// widths up to the whole basis leave every iteration count of the C2 problem unchanged).  Warp 0 (the main warp) runs
+// everything else of the sweep unchanged; warps 1-3 wait at a named barrier for its commands.
+#define QGD_TEAM_WARPS 4
+enum { TEAM_CMD_GS = 1, TEAM_CMD_UPD = 2, TEAM_CMD_EXIT = 3 };
+
+template <int EL>
+struct TeamView {
+  int* cmd;      // [0] command, [1] k (GS) or width (UPD), [2] index of a basis vector waiting in VN for its owner (-1: none)
+  double2* W;    // the vector being orthogonalised
+  double2* VN;   // a new basis vector on its way to the tensor memory of its owner
+  double2* C;    // [2][4] update parts, double buffered over the super-blocks
+  double* T;     // [3] transposition buffers of the helper warps (the main warp uses its gather buffer)
+};
+template <int EL>
+__host__ __device__ constexpr int team_doubles() { return 4 + 10 * (2 * 32 * EL) + 3 * 256; }
+template <int EL>
+__device__ __forceinline__ TeamView<EL> team_view(double* base) {
+  constexpr int VD = 2 * 32 * EL;
+  TeamView<EL> t;
+  t.cmd = reinterpret_cast<int*>(base);
+  t.W = reinterpret_cast<double2*>(base + 4);
+  t.VN = reinterpret_cast<double2*>(base + 4 + VD);
+  t.C = reinterpret_cast<double2*>(base + 4 + 2 * VD);
+  t.T = base + 4 + 10 * VD;
+  return t;
+}
+__device__ __forceinline__ void team_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ int team_owner(int i) { return (i >> 3) & 3; }
+__device__ __forceinline__ int team_slot(int i) { return ((i >> 5) << 3) + (i & 7); }
+
+// The block of warp `wid` in super-block `sb`: coefficients into hcol, update part into Cdst.
+template <int EL>
+__device__ __forceinline__ void team_block(uint32_t tm_own, int wid, int sb, int k, const Vec<EL>& w, double* T, double* hcol,
+                                           double2* Cdst, int lane) {
+  const int i0 = 8 * (4 * sb + wid);
+  Vec<EL> corr;
+  vzero(corr);
+  if (i0 < k) {
+    Vec<EL> vb[8];
+    uint32_t r[4 * EL * 8];
+    tmem_ld<4 * EL * 8>(tm_own + 4 * EL * (8 * sb), r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int e = 0; e < EL; ++e) {
+        vb[q].u[e] = d2(r[4 * EL * q + 4 * e], r[4 * EL * q + 4 * e + 1]);
+        vb[q].v[e] = d2(r[4 * EL * q + 4 * e + 2], r[4 * EL * q + 4 * e + 3]);
+      }
+    double h[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) h[q] = vdot_local<EL>(vb[q], w);
+    __syncwarp();
+    block_allsum8_smem(h, T, hcol + i0, lane);
+    const int nb = k - i0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < nb) vaxpy(corr, h[q], vb[q]);
+  }
+  v2_store<EL>(Cdst, corr, lane);
+}
+
+template <int EL>
+__device__ __forceinline__ void team_apply_parts(const double2* Cpar, Vec<EL>& w, int lane) {
+#pragma unroll
+  for (int wid = 0; wid < QGD_TEAM_WARPS; ++wid) {
+    Vec<EL> cw;
+    v2_load<EL>(cw, Cpar + (size_t)wid * 32 * EL, lane);
+    vaxpy(w, -1.0, cw);
+  }
+}
+
+// main warp: orthogonalise w against V[:, 0..k-1]; coefficients in c.hcol[0..k)
+template <int EL>
+__device__ __forceinline__ void gs_team_main(const FastCtx<EL>& c, int k, Vec<EL>& w, int pending) {
+  const TeamView<EL> tv = team_view<EL>(c.team);
+  const int lane = c.lane;
+  v2_store<EL>(tv.W, w, lane);
+  if (lane == 0) { tv.cmd[0] = TEAM_CMD_GS; tv.cmd[1] = k; tv.cmd[2] = pending; }
+  team_bar();
+  const int nsb = (((k + 7) >> 3) + 3) >> 2;
+  for (int sb = 0; sb < nsb; ++sb) {
+    double2* Cpar = tv.C + (size_t)(sb & 1) * QGD_TEAM_WARPS * 32 * EL;
+    team_block<EL>(c.tm, 0, sb, k, w, reinterpret_cast<double*>(c.xs), c.hcol, Cpar, lane);
+    team_bar();
+    team_apply_parts<EL>(Cpar, w, lane);
+  }
+}
+
+// main warp: x += V[:, 0..width-1] y with y in c.g (shared memory)
+template <int EL>
+__device__ __forceinline__ void update_team_main(const FastCtx<EL>& c, int width, Vec<EL>& x, int pending) {
+  const TeamView<EL> tv = team_view<EL>(c.team);
+  const int lane = c.lane;
+  if (lane == 0) { tv.cmd[0] = TEAM_CMD_UPD; tv.cmd[1] = width; tv.cmd[2] = pending; }
+  team_bar();
+  for (int j0 = 0; j0 < width; j0 += 32)   // blocks j0/8 + 0 of each super-block belong to warp 0
+    for (int q = 0; q < 8 && j0 + q < width; ++q) {
+      Vec<EL> vj;
+      tmem_load<EL>(c.tm + 4 * EL * team_slot(j0 + q), vj);
+      vaxpy(x, c.g[j0 + q], vj);
+    }
+  team_bar();
+#pragma unroll
+  for (int wid = 1; wid < QGD_TEAM_WARPS; ++wid) {
+    Vec<EL> cw;
+    v2_load<EL>(cw, tv.C + (size_t)wid * 32 * EL, lane);
+    vaxpy(x, 1.0, cw);
+  }
+}
+
+template <int EL>
+__device__ __forceinline__ void basis_store_team(const FastCtx<EL>& c, int i, const Vec<EL>& a, int& pending) {
+  if (team_owner(i) == 0) { tmem_store<EL>(c.tm + 4 * EL * team_slot(i), a); }
+  else { v2_store<EL>(team_view<EL>(c.team).VN, a, c.lane); pending = i; }
+}
+
+// helper warps 1..3: serve the main warp's commands until it says EXIT
+template <int EL>
+__device__ void team_helper_loop(double* team_base, double* hcol, const double* g, uint32_t tm_own, int wid, int lane) {
+  const TeamView<EL> tv = team_view<EL>(team_base);
+  double* T = tv.T + (size_t)(wid - 1) * 256;
+  for (;;) {
+    team_bar();
+    const int cmd = tv.cmd[0], arg = tv.cmd[1], pend = tv.cmd[2];
+    if (cmd == TEAM_CMD_EXIT) break;
+    if (pend >= 0 && team_owner(pend) == wid) {
+      Vec<EL> vn;
+      v2_load<EL>(vn, tv.VN, lane);
+      tmem_store<EL>(tm_own + 4 * EL * team_slot(pend), vn);
+    }
+    if (cmd == TEAM_CMD_GS) {
+      const int k = arg;
+      Vec<EL> w;
+      v2_load<EL>(w, tv.W, lane);
+      const int nsb = (((k + 7) >> 3) + 3) >> 2;
+      for (int sb = 0; sb < nsb; ++sb) {
+        double2* Cpar = tv.C + (size_t)(sb & 1) * QGD_TEAM_WARPS * 32 * EL;
+        team_block<EL>(tm_own, wid, sb, k, w, T, hcol, Cpar + (size_t)wid * 32 * EL, lane);
+        team_bar();
+        if (sb + 1 < nsb) team_apply_parts<EL>(Cpar, w, lane);
+      }
+    } else {  // TEAM_CMD_UPD
+      const int width = arg;
+      Vec<EL> part;
+      vzero(part);
+      for (int j0 = 8 * wid; j0 < width; j0 += 32)
+        for (int q = 0; q < 8 && j0 + q < width; ++q) {
+          Vec<EL> vj;
+          tmem_load<EL>(tm_own + 4 * EL * team_slot(j0 + q), vj);
+          vaxpy(part, g[j0 + q], vj);
+        }
+      v2_store<EL>(tv.C + (size_t)wid * 32 * EL, part, lane);
+      team_bar();
+    }
+  }
+}
+
 // ---- asynchronous 8-byte copies L2 -> shared memory (cp.async, SASS LDGSTS) -----------------------------
 __device__ __forceinline__ void cp8(double* dst_smem, const double* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -1247,9 +1419,10 @@ __device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double be
 }
 
 // GMRES with the blocked orthogonalisation; same interface and iteration semantics as gmres_fast_strict.
-template <int EL, int NC, int VARIANT, class OP>
+template <int EL, int NC, int VARIANT, bool TEAM, class OP>
 __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
                                   int restart, int maxiter) {
+  int pending = -1;  // TEAM: index of a basis vector handed to its owner warp with the next command
   constexpr int BLK = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 4;
   constexpr int CHK = 2 * EL;  // k <= restart <= 2N <= 64 EL: CHK chunks of 32 rows cover a Hessenberg column
   const int lane = c.lane;
@@ -1272,7 +1445,8 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
       const double beta2 = warp_allsum(vdot_local<EL>(v, v));
       const double rbeta = rsqrt(beta2);
       vscale(v, rbeta);
-      basis_store<EL>(c, 0, v);
+      if constexpr (TEAM) basis_store_team<EL>(c, 0, v, pending);
+      else basis_store<EL>(c, 0, v);
       accum = 1.0; res_beta = beta2 * rbeta; res_beta2 = beta2;
       if (first) conv = !(beta2 > tol2);  // at a restart residual.current keeps its value, as in the package
       first = false; start = false;
@@ -1284,7 +1458,8 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
       continue;
     }
     precond_fast<EL, NC>(R, w);  // expand!
-    if constexpr (QGD_GS_SUPER > 0 && BLK == 8) { __syncwarp(); gs_orthogonalize_super<EL, QGD_GS_SUPER>(c, k, w); }
+    if constexpr (TEAM) { __syncwarp(); gs_team_main<EL>(c, k, w, pending); pending = -1; __syncwarp(); }
+    else if constexpr (QGD_GS_SUPER > 0 && BLK == 8) { __syncwarp(); gs_orthogonalize_super<EL, QGD_GS_SUPER>(c, k, w); }
     else gs_orthogonalize<EL, BLK, VARIANT>(c, k, w);
     if constexpr ((VARIANT & 4) != 0) __syncwarp();  // lane 0's coefficient stores (block_allsum8_dmma) before c.hcol is read
     // ||w||^2 and the null-vector recurrence <nullvec[0..k), H[0..k, k-1]> (update_residual!)
@@ -1299,9 +1474,12 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
     }
     const double nrm2 = warp_allsum(vdot_local<EL>(w, w));
     const double dsum = warp_allsum(dpart);
-    const double rnrm = rsqrt(nrm2), nrm = nrm2 * rnrm;
+    // an exactly vanishing w (Krylov space exhausted, happy breakdown) gives H[k+1][k] = 0 as in the reference -- whose
+    // residual estimate then drops to zero and ends the solve -- not 0 * inf
+    const double rnrm = rsqrt(nrm2), nrm = nrm2 > 0.0 ? nrm2 * rnrm : 0.0;
     vscale(w, rnrm);
-    basis_store<EL>(c, k, w);
+    if constexpr (TEAM) basis_store_team<EL>(c, k, w, pending);
+    else basis_store<EL>(c, k, w);
     const double nv = -(dsum * rnrm);
     {  // Hessenberg column k-1 (rows 0..k) to the packed matrix in L2
       double* hc = c.Rg + hpk(k - 1);
@@ -1327,13 +1505,18 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
       const int width = k - 1;
       if constexpr (QGD_QR_LEAN) qr_solve_lean(c, width, res_beta);
       else qr_solve_fast(c, width, res_beta);
-      Vec<EL> vi;
-      basis_load<EL>(c, 0, vi);
-      for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 0..width-1] y
-        Vec<EL> vn;
-        if (j + 1 < width) basis_load<EL>(c, j + 1, vn);
-        vaxpy(x, c.g[j], vi);
-        if (j + 1 < width) vi = vn;
+      if constexpr (TEAM) {
+        update_team_main<EL>(c, width, x, pending);
+        pending = -1;
+      } else {
+        Vec<EL> vi;
+        basis_load<EL>(c, 0, vi);
+        for (int j = 0; j < width; ++j) {  // update_solution!: x += V[:, 0..width-1] y
+          Vec<EL> vn;
+          if (j + 1 < width) basis_load<EL>(c, j + 1, vn);
+          vaxpy(x, c.g[j], vi);
+          if (j + 1 < width) vi = vn;
+        }
       }
       __syncwarp();
       if (done) break;
@@ -1343,10 +1526,10 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
   return it;
 }
 
-template <int EL, int NC, int VARIANT, bool STRICT, class OP>
+template <int EL, int NC, int VARIANT, bool STRICT, bool TEAM, class OP>
 __device__ __forceinline__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b,
                                           double tol, int restart, int maxiter) {
-  if constexpr (QGD_MGS_BLOCK > 1 && !STRICT) return gmres_fast_blocked<EL, NC, VARIANT, OP>(c, R, op, x, b, tol, restart, maxiter);
+  if constexpr (QGD_MGS_BLOCK > 1 && !STRICT) return gmres_fast_blocked<EL, NC, VARIANT, TEAM, OP>(c, R, op, x, b, tol, restart, maxiter);
   else return gmres_fast_strict<EL, NC, OP>(c, R, op, x, b, tol, restart, maxiter);
 }
 
@@ -1419,18 +1602,20 @@ __device__ __forceinline__ void load_cv_fast(const FastCtx<EL>& c, const double*
 
 // shared-memory carve-up: [16 bytes: TMEM address slot][warp regions]; each region = fixed part + KS basis
 // vectors (+ extra doubles)
-template <int EL, int M, int NC, bool STRICT = false>
+template <int EL, int M, int NC, bool STRICT = false, bool TEAM = false>
 __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra,
                                                      uint32_t tmem_base) {
   FastCtx<EL> c;
   c.lane = threadIdx.x & 31;
   c.N = d.N; c.N2 = d.N2; c.KS = a.ks;
-  const int warp = threadIdx.x >> 5;
+  // TEAM: the four warps of the CTA serve ONE column: they share the (single) per-warp region; each owns a TMEM lane quarter
+  const int warp = TEAM ? 0 : (int)(threadIdx.x >> 5);
   // TMEM: warp w may address lanes [32 (w % 4), +32); warps w and w + 4 split the 512 columns
   const int groups = ((blockDim.x >> 5) + 3) >> 2;
   const int cols = a.tmem_cols / groups;
   c.KT = a.kt;
   c.tm = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cols * (warp >> 2));
+  if constexpr (TEAM) c.tm = tmem_base + ((uint32_t)(32 * (threadIdx.x >> 5)) << 16);
   double* w = reinterpret_cast<double*>(smem + 16) + (size_t)warp * a.warp_smem_doubles;
   c.xs = reinterpret_cast<double2*>(w); w += FastCtx<EL>::kRingDoubles;
   c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
@@ -1453,8 +1638,10 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   c.Vs = reinterpret_cast<double2*>(w); w += (size_t)a.ks * 2 * 32 * EL;
   double* hs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w) + 31) & ~(uintptr_t)31);  // 32-byte aligned columns (hpk)
   w += a.h_smem_doubles;
+  c.team = nullptr;
+  if constexpr (TEAM) { c.team = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w) + 15) & ~(uintptr_t)15); w = c.team + team_doubles<EL>(); }
   *extra = w;
-  const size_t slot = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const size_t slot = TEAM ? (size_t)blockIdx.x : (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
   c.Vg = reinterpret_cast<double2*>(a.Vws + slot * a.v_stride);
   c.Rg = a.h_smem_doubles ? hs : a.Hws + slot * a.h_stride;
   return c;
@@ -1464,12 +1651,20 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
 // FORCED: forced forward solves -- eval_forward!(...; forcing) with an explicit forcing array (a.forcing_in), or the P x ncol
 // forced solves of eval_grad_forced (a.base_history: item b is control parameter b, zero initial state, control vector 0,
 // the guard-penalty derivative accumulated on the way, no history written).
-template <int EL, int M, int NC, bool STRICT, bool FORCED = false>
+// TEAM: the latency team above -- a CTA of four warps per column; warps 1-3 only serve the orthogonalisation.
+template <int EL, int M, int NC, bool STRICT, bool FORCED = false, bool TEAM = false>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT>(d, a, smem, &extra, tmem_base);
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT, TEAM>(d, a, smem, &extra, tmem_base);
+  if constexpr (TEAM) {
+    if ((threadIdx.x >> 5) > 0) {
+      team_helper_loop<EL>(c.team, c.hcol, c.g, c.tm, (int)(threadIdx.x >> 5), c.lane);
+      tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
+      return;
+    }
+  }
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2;
   RegOps<EL, NC> R;
@@ -1555,7 +1750,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
         vaxpy(rhs, -1.0, fh);
       }
       x = guess;
-      const int it = gmres_fast<EL, NC, QGD_FWD_VARIANT, STRICT>(c, R, op, x, rhs, d.abstol, N2, N2);
+      const int it = gmres_fast<EL, NC, QGD_FWD_VARIANT, STRICT, TEAM>(c, R, op, x, rhs, d.abstol, N2, N2);
       if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
     }
     vstore(x, carry, N, lane);
@@ -1567,6 +1762,10 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
       }
     }
     publish_segment(a.progress + item, seg, lane);
+  }
+  if constexpr (TEAM) {  // release the helper warps
+    if (lane == 0) team_view<EL>(c.team).cmd[0] = TEAM_CMD_EXIT;
+    team_bar();
   }
   if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }
@@ -1623,13 +1822,20 @@ __device__ __forceinline__ void accumulate_grad_fast(int lane, int P, const QgdD
   }
 }
 
-template <int EL, int M, int NC, bool STRICT>
+template <int EL, int M, int NC, bool STRICT, bool TEAM = false>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
                                                                                const QgdDevControl* __restrict__ ctrls) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT>(d, a, smem, &extra, tmem_base);
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT, TEAM>(d, a, smem, &extra, tmem_base);
+  if constexpr (TEAM) {
+    if ((threadIdx.x >> 5) > 0) {
+      team_helper_loop<EL>(c.team, c.hcol, c.g, c.tm, (int)(threadIdx.x >> 5), c.lane);
+      tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
+      return;
+    }
+  }
   const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
   const int N = d.N, N2 = d.N2, Nt = d.nsteps + 1, P = d.P;
   RegOps<EL, NC> R0;
@@ -1770,7 +1976,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
           rhs.v[e] = fma(fsc, R.wv[e] * w0.v[e], rhs.v[e]);
         }
         // x0 = lambda_{n+1} (forward_evolution.jl:450)
-        const int it = gmres_fast<EL, NC, QGD_BWD_VARIANT, STRICT>(c, R, op, lam, rhs, d.abstol, N2, N2);
+        const int it = gmres_fast<EL, NC, QGD_BWD_VARIANT, STRICT, TEAM>(c, R, op, lam, rhs, d.abstol, N2, N2);
         if (lam0) vstore(lam, lam0 + (size_t)N2 * n, N, lane);
         if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
       }
@@ -1781,6 +1987,10 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
 #endif
     if (seg < nseg - 1) vstore(lam, carry, N, lane);
     publish_segment(a.progress + item, seg, lane);
+  }
+  if constexpr (TEAM) {  // release the helper warps
+    if (lane == 0) team_view<EL>(c.team).cmd[0] = TEAM_CMD_EXIT;
+    team_bar();
   }
   if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }

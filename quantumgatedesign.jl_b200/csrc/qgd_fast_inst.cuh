@@ -60,6 +60,26 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   return L;
 }
 
+// Latency team (qgd_fast.cuh): one CTA of four warps per column, the whole Krylov basis in the four TMEM lane quarters, the
+// packed Hessenberg matrix and the team's exchange buffers in shared memory.
+template <class K>
+FastCfg plan_fast_team(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t items, int restart) {
+  const size_t max_smem = h->prop.sharedMemPerBlockOptin;
+  FastCfg L{};
+  L.wpc = QGD_TEAM_WARPS;
+  L.threads = 32 * QGD_TEAM_WARPS;
+  L.kt = 64; L.ks = 0; L.tmem_cols = 512;
+  if (restart + 1 > QGD_TEAM_WARPS * 64) throw QgdError(QGD_EUNSUPPORTED, "latency team: Krylov basis larger than the tensor memory of four warps");
+  L.h_smem = (int)(((long)hpk(restart) + 8 + 3) & ~3L);
+  const int team = el == 1 ? team_doubles<1>() : team_doubles<2>();
+  L.warp_doubles = ((fixed_doubles + 1) & ~1) + L.h_smem + team + 8;
+  L.smem = 16 + (size_t)L.warp_doubles * 8;
+  if (L.smem > max_smem) throw QgdError(QGD_EUNSUPPORTED, "latency team: shared memory too small");
+  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  L.grid = (int)std::max<size_t>(1, std::min<size_t>(items, (size_t)h->prop.multiProcessorCount));
+  return L;
+}
+
 // The Krylov tail and the packed Hessenberg matrices of all resident warps live in ONE allocation (d_V) so that a
 // single L2 access-policy window can cover them (launch_sweep below).
 void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, SweepArgs& a) {
@@ -151,6 +171,20 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
 #define QGD_FAST_CASE_BWD(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC, false>(h, d, a); return true; }
 #define QGD_FAST_CASE_FWD_S(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC, true>(h, d, a); return true; }
 #define QGD_FAST_CASE_FWD_F(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_t<EL, M, NC, false, true>(h, d, a); return true; }
+template <int EL, int M, int NC>
+void launch_forward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  FastCfg L = plan_fast_team(h, k_forward_fast<EL, M, NC, false, false, true>, fast_fixed_doubles<EL, M, NC, false>(d.N2), EL, (size_t)a.B * d.ncol, d.N2);
+  ensure_krylov_fast(h, L, EL, d.N2, a);
+  launch_sweep(h, k_forward_fast<EL, M, NC, false, false, true>, L, d, a);
+}
+template <int EL, int M, int NC>
+void launch_backward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  FastCfg L = plan_fast_team(h, k_backward_fast<EL, M, NC, false, true>, fast_fixed_doubles<EL, M, NC, false>(d.N2), EL, (size_t)a.B * d.ncol, d.N2);
+  ensure_krylov_fast(h, L, EL, d.N2, a);
+  launch_sweep(h, k_backward_fast<EL, M, NC, false, true>, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
+}
+#define QGD_FAST_CASE_FWD_T(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_team_t<EL, M, NC>(h, d, a); return true; }
+#define QGD_FAST_CASE_BWD_T(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_team_t<EL, M, NC>(h, d, a); return true; }
 #define QGD_FAST_CASE_BWD_S(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC, true>(h, d, a); return true; }
 #define QGD_FAST_CASE_DER(EL, M, NC) if (el == EL && nc == NC) { launch_derivs_fast_t<EL, M, NC>(h, d, a, uv, ncols, cv, adjoint); return true; }
 
@@ -180,4 +214,13 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
 #define QGD_DEFINE_FAST_LAUNCHERS_FORCED(M)                                                                                 \
   bool launch_forward_fast_forced_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                       \
     QGD_FAST_SHAPES(QGD_FAST_CASE_FWD_F, M) return false;                                                                   \
+  }
+
+// The latency team (four warps per column) in translation units of its own.
+#define QGD_DEFINE_FAST_LAUNCHERS_TEAM(M)                                                                                   \
+  bool launch_forward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                         \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_FWD_T, M) return false;                                                                   \
+  }                                                                                                                         \
+  bool launch_backward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                        \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_BWD_T, M) return false;                                                                   \
   }

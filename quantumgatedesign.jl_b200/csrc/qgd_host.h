@@ -138,7 +138,9 @@ QGD_DECLARE_LAUNCHERS(8)
                                const double* cv, int adjoint);                                                     \
   bool launch_forward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);              \
   bool launch_backward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);             \
-  bool launch_forward_fast_forced_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);
+  bool launch_forward_fast_forced_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);              \
+  bool launch_forward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                \
+  bool launch_backward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);
 QGD_DECLARE_FAST_LAUNCHERS(1)
 QGD_DECLARE_FAST_LAUNCHERS(2)
 QGD_DECLARE_FAST_LAUNCHERS(3)

@@ -212,10 +212,14 @@ def test_save_every_nsteps(q, O):
     h.close()
 
 
-def test_full_cnot3_order8(q, O):
-    """BASELINE C2 at full size (N=64, nic=8, nsteps=550, order 8, P=180), parity run at abstol 1e-14."""
+@pytest.mark.parametrize("team", [2, 1])
+def test_full_cnot3_order8(q, O, team):
+    """BASELINE C2 at full size (N=64, nic=8, nsteps=550, order 8, P=180), parity run at abstol 1e-14: on the throughput
+    kernels (one warp per column, what a full batch runs on; team = 2) and on the four-warp latency team (what ONE
+    evaluation takes by default; team = 1)."""
     prob, controls, pcof, target, order = q.configs.cnot3(nsteps=550, tf=550.0, gmres_tol=1e-14)
     h = q.Handle(prob, controls)
+    h.set_option(q.backend.OPT_LATENCY_TEAM, team)
     out = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
     ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
     mism_f = int((out["iters_fwd"][:, :, 0] != ref["iters_fwd"]).sum())
@@ -381,7 +385,10 @@ def test_host_table_controls_match_device_controls(q, O, name):
     rng = np.random.default_rng(11)
     pcofs = np.stack([pcof, pcof * (1.0 + 0.3 * rng.standard_normal(len(pcof)))], axis=1)
     hd = q.Handle(prob, controls)
+    team = hd.discrete_adjoint(pcofs, q.complex_to_real(target), order=order)  # default for this few columns: the latency team
+    hd.set_option(q.backend.OPT_LATENCY_TEAM, 2)                              # one warp per column, blocks of 8
     direct = hd.discrete_adjoint(pcofs, q.complex_to_real(target), order=order)
+    assert rel(team["grad"], direct["grad"]) < RTOL
     cvals, table = _tables_from_device(hd, pcofs, prob.nsteps, prob.tf, m)
     host_controls = [q.HostEvaluatedControl(c.N_coeff, c.tf, None) for c in cl]
     hh = q.Handle(prob, host_controls)

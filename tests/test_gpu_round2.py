@@ -75,11 +75,15 @@ def test_strict_mgs_option_gives_equal_iteration_counts(q, O, name):
     assert np.array_equal(out["iters_term"][:, 0], ref["iters_term"])
     assert rel(out["grad"][:, 0], ref["grad"]) < RTOL
     assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
-    # and the default (blocked) orthogonalisation on the same handle: same numbers to the parity tolerance
+    # and the two default orthogonalisations on the same handle -- blocks of 8 on one warp per column (throughput kernels,
+    # team = 2) and super-blocks of 32 on the four-warp latency team (team = 1): same numbers to the parity tolerance
     h.set_option(q.backend.OPT_STRICT_MGS, 0)
-    blk = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
-    assert rel(blk["grad"][:, 0], out["grad"][:, 0]) < RTOL
-    assert np.abs(blk["iters_fwd"] - out["iters_fwd"]).max() <= 1 and np.abs(blk["iters_adj"] - out["iters_adj"]).max() <= 1
+    for team in (2, 1):
+        h.set_option(q.backend.OPT_LATENCY_TEAM, team)
+        blk = h.discrete_adjoint(pcof, q.complex_to_real(target), order=order, want_iters=True)
+        assert h.stats()["fast_path_launches"] == 2
+        assert rel(blk["grad"][:, 0], out["grad"][:, 0]) < RTOL
+        assert np.abs(blk["iters_fwd"] - out["iters_fwd"]).max() <= 1 and np.abs(blk["iters_adj"] - out["iters_adj"]).max() <= 1
     h.close()
 
 
@@ -478,6 +482,7 @@ def test_two_warps_per_sm_launch_shape_equals_single_evaluations(q):
     pcs = np.asfortranarray(np.stack([q.configs.cnot3_pcof(P, s) for s in range(30)], axis=1))
     tgt = q.complex_to_real(target)
     h = q.Handle(prob, controls)
+    h.set_option(q.backend.OPT_LATENCY_TEAM, 2)  # the single evaluations on the same kernel family as the batch (not the latency team)
     for strict in (0, 1):
         h.set_option(q.backend.OPT_STRICT_MGS, strict)
         batch = h.discrete_adjoint(pcs, tgt, order=order, want_iters=True)
@@ -501,10 +506,14 @@ def test_c3_full_batch_of_1024_control_vectors_matches_single_evaluations(q):
     h = q.Handle(prob, controls)
     batch = h.discrete_adjoint(pcs, tgt, order=order)
     assert np.isfinite(batch["grad"]).all() and (batch["infidelity"] > 0).all() and (batch["infidelity"] < 1.0 + 1e-9).all()
+    h.set_option(q.backend.OPT_LATENCY_TEAM, 2)  # single evaluations on the kernels the batch ran on: bit for bit
     for b in (0, 511, 1023):
         one = h.discrete_adjoint(pcs[:, b], tgt, order=order)
         assert np.array_equal(one["grad"][:, 0], batch["grad"][:, b])
         assert one["infidelity"][0] == batch["infidelity"][b] and one["guard_penalty"][0] == batch["guard_penalty"][b]
+    h.set_option(q.backend.OPT_LATENCY_TEAM, 0)  # and on the latency team a single evaluation takes by default: to the parity tolerance
+    one = h.discrete_adjoint(pcs[:, 511], tgt, order=order)
+    assert rel(one["grad"][:, 0], batch["grad"][:, 511]) < RTOL and abs(one["infidelity"][0] - batch["infidelity"][511]) <= RTOL
     h.close()
 
 
@@ -555,3 +564,36 @@ def test_optimize_gate_reduces_objective_and_reuses_the_resident_history(q, O):
     assert abs(res["final_infidelity"] - ref["infidelity"]) <= 1e-9 * max(abs(ref["infidelity"]), 1e-3)
     assert abs(res["final_guard_penalty"] - ref["guard_penalty"]) <= 1e-9 * max(abs(ref["guard_penalty"]), 1e-6)
     q.backend.clear_handles()
+
+
+# ---- the latency team: four warps per column ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cnot2", "cnot3_333", "cnot3_444_short", "cnot3_444_tol13"])
+def test_latency_team_vs_oracle_and_throughput_kernels(q, O, name):
+    """QGD_OPT_LATENCY_TEAM: one column on four warps (Krylov basis dealt out in blocks of 8 over the four TMEM lane quarters,
+    coefficients of a super-block of 32 from the same vector).  Against the oracle (equal GMRES iteration counts on these cases)
+    and against the one-warp-per-column kernels; selected automatically for up to one column per SM, never when more are in
+    flight; batches of independent control vectors give the same numbers as single evaluations."""
+    prob, controls, pcof, target, order = _fast_cases(q)[name]
+    tgt = q.complex_to_real(target)
+    h = q.Handle(prob, controls)
+    auto = h.discrete_adjoint(pcof, tgt, order=order, want_iters=True)            # default: nic columns <= 148 SMs -> team
+    h.set_option(q.backend.OPT_LATENCY_TEAM, 1)
+    team = h.discrete_adjoint(pcof, tgt, order=order, want_iters=True)
+    assert np.array_equal(auto["grad"], team["grad"]) and np.array_equal(auto["iters_adj"], team["iters_adj"])
+    h.set_option(q.backend.OPT_LATENCY_TEAM, 2)
+    one = h.discrete_adjoint(pcof, tgt, order=order, want_iters=True)
+    assert not np.array_equal(one["grad"], team["grad"]) or name == "cnot2"       # really another kernel (summation order differs)
+    assert rel(team["grad"], one["grad"]) < RTOL
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    assert np.array_equal(team["iters_fwd"][:, :, 0], ref["iters_fwd"]) and np.array_equal(team["iters_adj"][:, :, 0], ref["iters_adj"])
+    assert rel(team["grad"][:, 0], ref["grad"]) < RTOL
+    assert abs(team["infidelity"][0] - ref["infidelity"]) <= RTOL * abs(ref["infidelity"])
+    assert abs(team["guard_penalty"][0] - ref["guard_penalty"]) <= RTOL * max(abs(ref["guard_penalty"]), 1e-300)
+    # a batch on the team equals its elements on the team, bit for bit
+    h.set_option(q.backend.OPT_LATENCY_TEAM, 1)
+    pcs = np.stack([pcof, 0.7 * pcof, -0.4 * pcof], axis=1)
+    batch = h.discrete_adjoint(pcs, tgt, order=order)
+    assert np.array_equal(batch["grad"][:, 0], team["grad"][:, 0])
+    again = h.discrete_adjoint(pcs[:, 2], tgt, order=order)
+    assert np.array_equal(batch["grad"][:, 2], again["grad"][:, 0])
+    h.close()
