@@ -583,6 +583,15 @@ bool try_backward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (team_wanted(h, a) && try_backward_fast_team(h, d, a)) return true;
   return h->opt[QGD_OPT_STRICT_MGS] ? try_backward_fast_strict(h, d, a) : try_backward_fast_default(h, d, a);
 }
+// terminal condition on the register operators (default orthogonalisation only: the strict option keeps the generic kernel,
+// whose Gram-Schmidt is the reference's one projection at a time)
+bool try_terminal_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  if (!fast_applicable(h, d.m) || h->opt[QGD_OPT_STRICT_MGS]) return false;
+  const int64_t sweeps = h->stats.fast_path_launches;  // that counter is for the two sweep kernels
+  const bool done = [&]() -> bool { QGD_FAST_SWITCH(d.m, launch_terminal_fast, h, d, a, h->fast_el, h->Nc) }();
+  h->stats.fast_path_launches = sweeps;
+  return done;
+}
 bool try_derivs_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a, double* uv, int ncols, const double* cv, int adjoint) {
   if (!fast_applicable(h, d.m)) return false;
   QGD_FAST_SWITCH(d.m, launch_derivs_fast, h, d, a, h->fast_el, h->Nc, uv, ncols, cv, adjoint)
@@ -682,7 +691,9 @@ void run_adjoint(qgd_handle* h, int B, int order, const double* d_target, bool w
   }
   const bool scalar_exchange = h->comm && h->opt[QGD_OPT_TERMINAL_EXCHANGE] == 1;
   if (scalar_exchange) { a.dots_in = h->d_dots.as<double>(); a.term_col0 = h->col0; a.term_ncol = h->ncol; }
-  if (scalar_exchange || !try_terminal_dense(h, d, a)) { QGD_DISPATCH_EL(el, launch_terminal, h, d, a); }
+  if (!try_terminal_fast(h, d, a)) {
+    if (scalar_exchange || !try_terminal_dense(h, d, a)) { QGD_DISPATCH_EL(el, launch_terminal, h, d, a); }
+  }
   a.iters = want_iters ? h->d_iters_a.as<int>() : nullptr;
   if (want_lambda0) {
     const size_t sz = (size_t)h->N2 * (h->nsteps + 1) * h->ncol * B * 8;

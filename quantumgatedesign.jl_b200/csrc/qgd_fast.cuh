@@ -605,7 +605,7 @@ __device__ __forceinline__ void mgs_step(int i, const Vec<EL>& vi, Vec<EL>& w, d
 // OP: apply(in, out) = A in; the left preconditioner is applied here.  Returns the number of iterations.
 template <int EL, int NC, class OP>
 __device__ int gmres_fast_strict(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
-                                 int restart, int maxiter) {
+                                 int restart, int maxiter, double reltol = -1.0) {
   const int lane = c.lane;
   Vec<EL> v, w;
   op.apply(x, w);
@@ -614,6 +614,9 @@ __device__ int gmres_fast_strict(const FastCtx<EL>& c, const RegOps<EL, NC>& R, 
   precond_fast<EL, NC>(R, v);
   double beta2 = warp_allsum(vdot_local<EL>(v, v));
   double rbeta = rsqrt(beta2), beta = beta2 * rbeta;
+  // reltol >= 0 (terminal-condition solves, gmres! driver): tol = max(reltol * ||initial residual||, tol) as IterativeSolvers
+  // sets it; the time-stepping solves pass -1 (fixed absolute tolerance)
+  if (reltol >= 0.0) tol = fmax(reltol * beta, tol);
   vscale(v, rbeta);
   basis_store<EL>(c, 0, v);
   double cur = beta, res_beta = beta, accum = 1.0, gcur = beta;
@@ -1428,7 +1431,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
   const int lane = c.lane;
   // residual estimate beta / sqrt(accum) against tol, tested as beta^2 <= tol^2 accum (no square root on the
   // critical path of an iteration; the two tests differ only when the estimate is within an ulp of tol)
-  const double tol2 = tol * tol;
+  double tol2 = tol * tol;
   double res_beta = 0.0, res_beta2 = 0.0, accum = 1.0;
   bool conv = false, first = true, start = true;
   int k = 1, it = 0;
@@ -1991,6 +1994,74 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
   if constexpr (TEAM) {  // release the helper warps
     if (lane == 0) team_view<EL>(c.team).cmd[0] = TEAM_CMD_EXIT;
     team_bar();
+  }
+  if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// Infidelity + terminal condition (src/infidelity.jl:7-18, src/eval_grad_discrete_adjoint.jl:1-67) on the register operators:
+// one warp per control vector; <psi_N, R>, <psi_N, T> over ALL columns, then per column the un-preconditioned GMRES(20) solve
+//   LHS(tf)^T lambda_N = (2 / N_ess^2) (<psi,R> R + <psi,T> T) - (dt / tf) W psi_N
+// with the solution of column i-1 as the initial guess of column i, as the reference carries it.  (The generic k_terminal does
+// the same through the row-ELL operators; at one evaluation it took 9 % of the call.)  The solve uses the STRICT Gram-Schmidt:
+// at 64 levels and tolerances of 1e-12 and below it runs into its 2N-iteration cap un-converged (in the reference too), and
+// the iterate it stops at then moves by 1e-5 relative under the blocked orthogonalisation's different rounding (measured,
+// DESIGN 9.2) -- which would shift every adjoint iteration count downstream.  It is one short solve per column.
+template <int EL, int M, int NC>
+__global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_terminal_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* extra;
+  const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
+  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, true>(d, a, smem, &extra, tmem_base);
+  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int N = d.N, N2 = d.N2;
+  RegOps<EL, NC> R;
+  load_regops<EL, NC>(R, d, lane, -1);  // no preconditioner in the terminal solves
+  double a_lhs[M + 1];
+#pragma unroll
+  for (int j = 0; j <= M; ++j) a_lhs[j] = d.a_lhs[j];
+  const AdjOpFast<EL, M, NC> op{c, R, a_lhs};
+  const size_t cv_stride = (size_t)2 * (M + 1) * NC;
+  const double ness2 = (double)d.Ness * (double)d.Ness, sc = 2.0 / ness2;
+  const double fsc = -2.0 * d.dt / d.tf * 0.5;  // forcing[:, end, :]: trapezoid weight 1/2
+  const int restart = N2 < 20 ? N2 : 20;
+  for (int b = blockIdx.x * wpc + warp; b < a.B; b += gridDim.x * wpc) {
+    const double* psi = a.final_all + (size_t)N2 * d.nic * b;
+    double dR = 0.0, dT = 0.0;
+    int tc0 = 0, tc1 = d.nic;
+    if (a.dots_in) {
+      dR = a.dots_in[2 * b]; dT = a.dots_in[2 * b + 1];
+      tc0 = a.term_col0; tc1 = a.term_col0 + a.term_ncol;
+    } else {
+      for (int col = 0; col < d.nic; ++col) {
+        Vec<EL> p, Rt;
+        vload(p, psi + (size_t)N2 * col, N, lane);
+        vload(Rt, a.target + (size_t)N2 * col, N, lane);
+#pragma unroll
+        for (int e = 0; e < EL; ++e) {
+          dR += p.u[e] * Rt.u[e] + p.v[e] * Rt.v[e];
+          dT += p.u[e] * Rt.v[e] - p.v[e] * Rt.u[e];  // T = [R_v; -R_u]
+        }
+      }
+      dR = warp_sum(dR);
+      dT = warp_sum(dT);
+    }
+    if (lane == 0) a.infidelity[b] = 1.0 - (dR * dR + dT * dT) / ness2;
+    load_cv_fast<EL, M, NC>(c, a.cvals + ((size_t)b * (d.nsteps + 1) + d.nsteps) * cv_stride);  // controls at t = tf
+    Vec<EL> x;
+    vzero(x);
+    for (int col = tc0; col < tc1; ++col) {
+      Vec<EL> p, Rt, rhs;
+      vload(p, psi + (size_t)N2 * col, N, lane);
+      vload(Rt, a.target + (size_t)N2 * col, N, lane);
+#pragma unroll
+      for (int e = 0; e < EL; ++e) {
+        rhs.u[e] = (dR * Rt.u[e] + dT * Rt.v[e]) * sc + fsc * (R.wu[e] * p.u[e]);
+        rhs.v[e] = (dR * Rt.v[e] + dT * (-Rt.u[e])) * sc + fsc * (R.wv[e] * p.v[e]);
+      }
+      const int it = gmres_fast_strict<EL, NC>(c, R, op, x, rhs, d.abstol, restart, N2, d.reltol);
+      vstore(x, a.terminal_out + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
+      if (a.iters_term && lane == 0) a.iters_term[(size_t)col + (size_t)d.nic * b] = it;
+    }
   }
   if (a.tmem_cols) tmem_free_cols(tmem_base, (uint32_t)a.tmem_cols);
 }

@@ -154,6 +154,13 @@ void launch_backward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   launch_sweep(h, k_backward_fast<EL, M, NC, STRICT>, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
 }
 template <int EL, int M, int NC>
+void launch_terminal_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  const int restart = std::min(20, d.N2);
+  FastCfg L = plan_fast(h, k_terminal_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC, true>(d.N2), EL, (size_t)a.B, 0, restart);
+  ensure_krylov_fast(h, L, EL, restart, a);
+  launch_sweep(h, k_terminal_fast<EL, M, NC>, L, d, a);
+}
+template <int EL, int M, int NC>
 void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, int ncols, const double* cv, int adjoint) {
   FastCfg L = plan_fast(h, k_derivs_fast<EL, M, NC>, fast_fixed_doubles<EL, M, NC>(d.N2), EL, (size_t)ncols, 0, 1);
   ensure_krylov_fast(h, L, EL, 1, a);
@@ -186,6 +193,7 @@ void launch_backward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
 #define QGD_FAST_CASE_FWD_T(EL, M, NC) if (el == EL && nc == NC) { launch_forward_fast_team_t<EL, M, NC>(h, d, a); return true; }
 #define QGD_FAST_CASE_BWD_T(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_team_t<EL, M, NC>(h, d, a); return true; }
 #define QGD_FAST_CASE_BWD_S(EL, M, NC) if (el == EL && nc == NC) { launch_backward_fast_t<EL, M, NC, true>(h, d, a); return true; }
+#define QGD_FAST_CASE_TRM(EL, M, NC) if (el == EL && nc == NC) { launch_terminal_fast_t<EL, M, NC>(h, d, a); return true; }
 #define QGD_FAST_CASE_DER(EL, M, NC) if (el == EL && nc == NC) { launch_derivs_fast_t<EL, M, NC>(h, d, a, uv, ncols, cv, adjoint); return true; }
 
 #define QGD_DEFINE_FAST_LAUNCHERS(M)                                                                                        \
@@ -198,6 +206,9 @@ void launch_backward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   bool launch_derivs_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc, double* uv, int ncols,          \
                                const double* cv, int adjoint) {                                                             \
     QGD_FAST_SHAPES(QGD_FAST_CASE_DER, M) return false;                                                                     \
+  }                                                                                                                         \
+  bool launch_terminal_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                             \
+    QGD_FAST_SHAPES(QGD_FAST_CASE_TRM, M) return false;                                                                     \
   }
 
 // The same sweeps with strict modified Gram-Schmidt (QGD_OPT_STRICT_MGS), in translation units of their own.

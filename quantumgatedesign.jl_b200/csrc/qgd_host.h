@@ -136,6 +136,7 @@ QGD_DECLARE_LAUNCHERS(8)
   bool launch_backward_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                    \
   bool launch_derivs_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc, double* uv, int ncols, \
                                const double* cv, int adjoint);                                                     \
+  bool launch_terminal_fast_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                    \
   bool launch_forward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);              \
   bool launch_backward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);             \
   bool launch_forward_fast_forced_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);              \
