@@ -294,9 +294,10 @@ void validate_and_load(qgd_handle* h, const qgd_problem_t* p) {
   }
 
   // ---- does the problem have the structure of the register-operator fast path?  diagonal drift, <= 2 entries per
-  // row and control operator, diagonal guard projector, N <= 64 (qgd_fast.cuh)
+  // row and control operator, diagonal guard projector; N <= 64 on one warp per column, N <= 256 on row-split groups of
+  // two or four warps (qgd_fast.cuh)
   {
-    bool ok = n <= 64 && h->Nc >= 1 && L.L[0] <= 1 && LW <= 1;
+    bool ok = n <= 256 && h->Nc >= 1 && L.L[0] <= 1 && LW <= 1;
     for (int k = 1; k < L.n_ops && ok; ++k) ok = L.L[k] <= 2;
     if (ok && L.L[0] == 1) {
       const int* col = reinterpret_cast<const int*>(h->blob.data() + L.off_col[0]);
@@ -309,6 +310,7 @@ void validate_and_load(qgd_handle* h, const qgd_problem_t* p) {
     }
     h->fast_ok = ok;
     h->fast_el = n <= 32 ? 1 : 2;
+    h->fast_rs = n <= 64 ? 1 : (n <= 128 ? 2 : 4);
   }
   // ---- dense problems whose level count is a multiple of 32: row-major dense copies for the tensor-core path
   // (qgd_dense.cu); "dense" = more than a quarter of the entries of some operator present
@@ -556,8 +558,14 @@ bool try_backward_fast_default(qgd_handle* h, const QgdDevProb& d, const SweepAr
 bool try_backward_fast_strict(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   QGD_FAST_SWITCH(d.m, launch_backward_fast_strict, h, d, a, h->fast_el, h->Nc)
 }
+bool try_forward_fast_rs(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_forward_fast_rs, h, d, a, h->fast_rs, h->Nc)
+}
+bool try_backward_fast_rs(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
+  QGD_FAST_SWITCH(d.m, launch_backward_fast_rs, h, d, a, h->fast_rs, h->Nc)
+}
 bool try_forward_fast_forced(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {  // forced solves: eval_forward!(...; forcing), eval_grad_forced
-  if (!fast_applicable(h, d.m)) return false;
+  if (!fast_applicable(h, d.m) || h->fast_rs > 1) return false;
   QGD_FAST_SWITCH(d.m, launch_forward_fast_forced, h, d, a, h->fast_el, h->Nc)
 }
 bool try_forward_fast_team(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
@@ -575,25 +583,28 @@ bool team_wanted(const qgd_handle* h, const SweepArgs& a) {
 // QGD_OPT_STRICT_MGS selects the strict modified Gram-Schmidt instantiation of the same sweeps
 bool try_forward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (!fast_applicable(h, d.m)) return false;
+  // 64 < N <= 256: row-split groups, default orthogonalisation only (the strict option keeps the generic kernels)
+  if (h->fast_rs > 1) return !h->opt[QGD_OPT_STRICT_MGS] && try_forward_fast_rs(h, d, a);
   if (team_wanted(h, a) && try_forward_fast_team(h, d, a)) return true;
   return h->opt[QGD_OPT_STRICT_MGS] ? try_forward_fast_strict(h, d, a) : try_forward_fast_default(h, d, a);
 }
 bool try_backward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
   if (!fast_applicable(h, d.m)) return false;
+  if (h->fast_rs > 1) return !h->opt[QGD_OPT_STRICT_MGS] && try_backward_fast_rs(h, d, a);
   if (team_wanted(h, a) && try_backward_fast_team(h, d, a)) return true;
   return h->opt[QGD_OPT_STRICT_MGS] ? try_backward_fast_strict(h, d, a) : try_backward_fast_default(h, d, a);
 }
 // terminal condition on the register operators (default orthogonalisation only: the strict option keeps the generic kernel,
 // whose Gram-Schmidt is the reference's one projection at a time)
 bool try_terminal_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
-  if (!fast_applicable(h, d.m) || h->opt[QGD_OPT_STRICT_MGS]) return false;
+  if (!fast_applicable(h, d.m) || h->opt[QGD_OPT_STRICT_MGS] || h->fast_rs > 1) return false;
   const int64_t sweeps = h->stats.fast_path_launches;  // that counter is for the two sweep kernels
   const bool done = [&]() -> bool { QGD_FAST_SWITCH(d.m, launch_terminal_fast, h, d, a, h->fast_el, h->Nc) }();
   h->stats.fast_path_launches = sweeps;
   return done;
 }
 bool try_derivs_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a, double* uv, int ncols, const double* cv, int adjoint) {
-  if (!fast_applicable(h, d.m)) return false;
+  if (!fast_applicable(h, d.m) || h->fast_rs > 1) return false;
   QGD_FAST_SWITCH(d.m, launch_derivs_fast, h, d, a, h->fast_el, h->Nc, uv, ncols, cv, adjoint)
 }
 

@@ -161,14 +161,28 @@ __device__ __forceinline__ void load_regops(RegOps<EL, NC>& R, const QgdDevProb&
 }
 
 // ---- per-warp context ----------------------------------------------------------------------------------
-template <int EL>
+// RS (row split, 1 / 2 / 4): the level rows of a column are dealt over RS warps of a CTA -- warp `slice` owns the rows
+// [32 EL slice, 32 EL (slice + 1)) with the SAME per-lane registers as a one-warp column (operators, state, its slice of
+// every Krylov vector in its own TMEM quarter / shared memory / L2 tail).  The warps of a group exchange the state for the
+// operator gathers through ONE shared gather buffer (gx) and complete every row-space reduction through gred, each
+// behind a named barrier of the group; all scalar work of GMRES (Hessenberg column, residual recurrence, least squares)
+// is replicated per warp from bitwise identical sums, so the warps of a group take every branch together.
+template <int EL, int RS = 1>
 struct FastCtx {
   int lane, N, N2;
+  int vl;         // row index of this lane's first element: lane + 32 EL slice  (row-space loads, stores, gathers)
+  int slice, bar; // RS > 1: position in the group, named barrier of the group
+  double2* gx;    // RS > 1: smem [2][32 EL RS] gather buffer of the group
+  double* gred;   // RS > 1: smem [2][RS][8] partial sums of the group (double buffered: one barrier per reduction)
+  unsigned* gtick;  // RS > 1: smem ticket word of the group
+  mutable unsigned par;  // RS > 1: parity of the next reduction
   int KT, KS;     // Krylov vectors [0,KT) live in TMEM, [KT,KT+KS) in shared memory, the rest in L2
   uint32_t tm;    // TMEM address of this warp's region (its 32 lanes, its column range)
   // xs: (u,v) gather buffers of the operator application (double buffered, 2 x 32 EL double2); the same storage is
   // the 8 x 32 transposition buffer of block_allsum and the cp.async ring of qr_solve_fast (>= 256 doubles)
-  static constexpr int kRingDoubles = 2 * 2 * 32 * EL < 256 ? 256 : 2 * 2 * 32 * EL;
+  static constexpr int kRS = RS;
+  static constexpr int kRing0 = 2 * 2 * 32 * EL < 256 ? 256 : 2 * 2 * 32 * EL;
+  static constexpr int kRingDoubles = RS == 1 ? kRing0 : (kRing0 > 64 * EL * RS + 2 ? kRing0 : 64 * EL * RS + 2);  // RS > 1: g [2N + 2]
   double2* xs;    // smem [kRingDoubles / 2]
   double2* cv;    // smem [M+1][NC]    (p_k^(d)/d!, q_k^(d)/d!) of the current time level
   double* nullv;  // smem [N2+2]       left null vector of the residual recurrence
@@ -181,16 +195,16 @@ struct FastCtx {
   double* Rg;     // global            packed upper-triangular R: column j at j(j+1)/2
   double* team;   // smem: shared state of the latency team (TeamView), null in the one-warp-per-column kernels
 };
-template <int EL, int M, int NC, bool STRICT = false>
+template <int EL, int M, int NC, bool STRICT = false, int RS = 1>
 __host__ __device__ constexpr int fast_fixed_doubles(int N2) {
 #if QGD_COMPACT_SMEM
   // strict kernels (progressive Givens): xs (+ gKs, gSs aliased) + cv + nullv + rot + g
-  if (STRICT) return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
+  if (STRICT) return FastCtx<EL, RS>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
   // xs (+ g, gKs, gSs aliased) + cv + nullv + hcol
-  return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + (N2 + 2 + 8);
+  return FastCtx<EL, RS>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + (N2 + 2 + 8);
 #else
   // xs + cv + nullv + rot + g
-  return FastCtx<EL>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
+  return FastCtx<EL, RS>::kRingDoubles + 2 * (M + 1) * NC + (N2 + 2) + 2 * (N2 + 2 + 8) + (N2 + 2);
 #endif
 }
 
@@ -213,6 +227,59 @@ template <int EL>
 __device__ __forceinline__ void v2_store(double2* p, const Vec<EL>& a, int lane) {
 #pragma unroll
   for (int e = 0; e < EL; ++e) p[lane + 32 * e] = make_double2(a.u[e], a.v[e]);
+}
+
+// ---- row-split groups (RS > 1) ---------------------------------------------------------------------------
+template <int EL, int RS>
+__device__ __forceinline__ void gsync(const FastCtx<EL, RS>& c) {
+  if constexpr (RS == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(c.bar), "n"(32 * RS) : "memory");
+}
+// gather buffer `which` (0 / 1) of the operator application: per warp, or the group's
+template <int EL, int RS>
+__device__ __forceinline__ double2* gather_buf(const FastCtx<EL, RS>& c, int which) {
+  if constexpr (RS == 1) return c.xs + which * 32 * EL;
+  else return c.gx + which * 32 * EL * RS;
+}
+// Sum of one double per lane over the ROWS of the column: over the warp, and for RS > 1 over the warps of the group -- every
+// warp adds the RS warp totals in slice order, so all of them hold the same bits.
+template <int EL, int RS>
+__device__ __forceinline__ double row_allsum(const FastCtx<EL, RS>& c, double p) {
+  const double t = warp_allsum(p);
+  if constexpr (RS == 1) return t;
+  else {
+    double* buf = c.gred + (c.par & 1u) * (RS * 8);
+    c.par ^= 1u;
+    if (c.lane == 0) buf[c.slice * 8] = t;
+    gsync(c);
+    double r = buf[0];
+#pragma unroll
+    for (int sl = 1; sl < RS; ++sl) r += buf[sl * 8];
+    return r;
+  }
+}
+// The same for the 8 coefficients of a Gram-Schmidt block: warp totals in slot[0..8) (shared memory, this warp's Hessenberg
+// column) on entry, group totals there and in p on return.
+template <int EL, int RS>
+__device__ __forceinline__ void row_combine8(const FastCtx<EL, RS>& c, double (&p)[8], double* slot) {
+  if constexpr (RS > 1) {
+    double* buf = c.gred + (c.par & 1u) * (RS * 8);
+    c.par ^= 1u;
+    if (c.lane < 8) buf[c.slice * 8 + c.lane] = slot[c.lane];
+    gsync(c);
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+      double2 t = reinterpret_cast<const double2*>(buf)[q >> 1];
+#pragma unroll
+      for (int sl = 1; sl < RS; ++sl) {
+        const double2 u = reinterpret_cast<const double2*>(buf + sl * 8)[q >> 1];
+        t.x += u.x; t.y += u.y;
+      }
+      p[q] = t.x; p[q + 1] = t.y;
+      if (c.lane == (q >> 1)) reinterpret_cast<double2*>(slot)[q >> 1] = t;
+    }
+    __syncwarp();
+  }
 }
 
 // z-sums of one vector (in the gather buffer): K_k x and S_k x restricted to this lane's rows.
@@ -250,11 +317,11 @@ struct FastForcing {
   int P, kop;         // kop: index (0-based) of the control operator of theta
 };
 
-template <int EL, int M, int NC, bool STEP, bool FORCE = false>
-__device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
+template <int EL, int M, int NC, bool STEP, bool FORCE = false, int RS>
+__device__ __forceinline__ void fwd_fast(const FastCtx<EL, RS>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
                                          Vec<EL>& out, const double* a_tay, Vec<EL>* guess, double* hist,
                                          const FastForcing* F = nullptr) {
-  const int lane = c.lane, N = c.N, N2 = c.N2;
+  const int lane = c.vl, N = c.N, N2 = c.N2;  // row space: lane + 32 EL slice
   Vec<EL> acc[M + 1];
 #pragma unroll
   for (int j = 1; j <= M; ++j) vzero(acc[j]);
@@ -264,14 +331,14 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
       for (int j = 0; j < M; ++j) vload_cg(acc[j + 1], F->arr + (size_t)j * N2, N, lane);
     }
     if (F->hb) {
-      __syncwarp();
+      gsync(c);
 #pragma unroll
       for (int i = 0; i < M; ++i) {
         Vec<EL> wi;
         vload_cg(wi, F->hb + (size_t)i * N2, N, lane);
-        double2* xb = c.xs + (i & 1) * 32 * EL;
+        double2* xb = gather_buf(c, i & 1);
         xs_store<EL>(xb, wi, lane);
-        __syncwarp();
+        gsync(c);
         ZS<EL, NC> z;
         zsums<EL, NC>(R, xb, z);
         double Ku[EL], Kv[EL], Su[EL], Sv[EL];
@@ -292,7 +359,7 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
           }
         }
       }
-      __syncwarp();
+      gsync(c);
     }
   }
   Vec<EL> w = x;
@@ -302,7 +369,7 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
     *guess = x;
     if (hist) vstore_cs(x, hist, N, lane);
   }
-  __syncwarp();
+  gsync(c);
 #pragma unroll
   for (int i = 0; i < M; ++i) {
     if (i > 0) {
@@ -315,9 +382,9 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
         if (hist) vstore_cs(w, hist + (size_t)i * N2, N, lane);
       }
     }
-    double2* xb = c.xs + (i & 1) * 32 * EL;
+    double2* xb = gather_buf(c, i & 1);
     xs_store<EL>(xb, w, lane);
-    __syncwarp();
+    gsync(c);
     ZS<EL, NC> z;
     zsums<EL, NC>(R, xb, z);
 #pragma unroll
@@ -355,11 +422,11 @@ __device__ __forceinline__ void fwd_fast(const FastCtx<EL>& c, const RegOps<EL, 
 // with w_i the forward Taylor columns of the same time level (hist, global).  SURVEY A.6.
 // LAST: this is the last use of the history level (evict-first load); otherwise the level is read once more by the
 // next adjoint step and is loaded with the default L2 policy so that it is still resident then.
-template <int EL, int M, int NC, bool GRAD>
-__device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
+template <int EL, int M, int NC, bool GRAD, int RS>
+__device__ __forceinline__ void adj_fast(const FastCtx<EL, RS>& c, const RegOps<EL, NC>& R, const Vec<EL>& x, const double* alpha,
                                          Vec<EL>& out, const double* hist, double (&gK)[M][NC], double (&gS)[M][NC],
                                          bool last_use = true) {
-  const int lane = c.lane, N = c.N, N2 = c.N2;
+  const int lane = c.vl, N = c.N, N2 = c.N2;  // row space: lane + 32 EL slice
   Vec<EL> what[M + 1];
 #pragma unroll
   for (int j = 0; j <= M; ++j) { what[j] = x; vscale(what[j], alpha[j]); }
@@ -374,12 +441,12 @@ __device__ __forceinline__ void adj_fast(const FastCtx<EL>& c, const RegOps<EL, 
       for (int i = 0; i < M; ++i) vload_cg(wh[i], hist + (size_t)i * N2, N, lane);
     }
   }
-  __syncwarp();
+  gsync(c);
 #pragma unroll
   for (int j = M - 1; j >= 0; --j) {
-    double2* xb = c.xs + (j & 1) * 32 * EL;
+    double2* xb = gather_buf(c, j & 1);
     xs_store<EL>(xb, what[j + 1], lane);
-    __syncwarp();
+    gsync(c);
     ZS<EL, NC> z;
     zsums<EL, NC>(R, xb, z);
     const double inv = 1.0 / (double)(j + 1);
@@ -494,14 +561,14 @@ __device__ __forceinline__ void tmem_load(uint32_t taddr, Vec<EL>& a) {
 }
 
 // ---- Krylov basis access: TMEM tier, shared-memory tier, L2 tail ---------------------------------------
-template <int EL>
-__device__ __forceinline__ void basis_load(const FastCtx<EL>& c, int i, Vec<EL>& a) {
+template <int EL, int RS>
+__device__ __forceinline__ void basis_load(const FastCtx<EL, RS>& c, int i, Vec<EL>& a) {
   if (i < c.KT) tmem_load<EL>(c.tm + 4 * EL * i, a);
   else if (i < c.KT + c.KS) v2_load<EL>(a, c.Vs + (size_t)(i - c.KT) * 32 * EL, c.lane);
   else v2_load_cg<EL>(a, c.Vg + (size_t)(i - c.KT - c.KS) * 32 * EL, c.lane);
 }
-template <int EL>
-__device__ __forceinline__ void basis_store(const FastCtx<EL>& c, int i, const Vec<EL>& a) {
+template <int EL, int RS>
+__device__ __forceinline__ void basis_store(const FastCtx<EL, RS>& c, int i, const Vec<EL>& a) {
   if (i < c.KT) tmem_store<EL>(c.tm + 4 * EL * i, a);
   else if (i < c.KT + c.KS) v2_store<EL>(c.Vs + (size_t)(i - c.KT) * 32 * EL, a, c.lane);
   else v2_store<EL>(c.Vg + (size_t)(i - c.KT - c.KS) * 32 * EL, a, c.lane);
@@ -554,8 +621,8 @@ __device__ __forceinline__ void givens_fast(double f, double g, double& cs, doub
 
 // Solve R y = g (R upper triangular, packed columns in L2 with RECIPROCAL diagonal), y overwrites c.g (shared).
 // Column j-1 is fetched while column j is being eliminated.
-template <int EL>
-__device__ __forceinline__ void trsv_fast(const FastCtx<EL>& c, int width) {
+template <int EL, int RS>
+__device__ __forceinline__ void trsv_fast(const FastCtx<EL, RS>& c, int width) {
   const int lane = c.lane;
   constexpr int CH = 4;  // rows handled per lane: width <= restart <= 128
   double cur[CH], nxt[CH], dcur, dnxt = 0.0;
@@ -603,8 +670,8 @@ __device__ __forceinline__ void mgs_step(int i, const Vec<EL>& vi, Vec<EL>& w, d
 
 // GMRES for the time-stepping solves (fixed absolute tolerance, restart = maxiter = 2N).
 // OP: apply(in, out) = A in; the left preconditioner is applied here.  Returns the number of iterations.
-template <int EL, int NC, class OP>
-__device__ int gmres_fast_strict(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
+template <int EL, int NC, class OP, int RS>
+__device__ int gmres_fast_strict(const FastCtx<EL, RS>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
                                  int restart, int maxiter, double reltol = -1.0) {
   const int lane = c.lane;
   Vec<EL> v, w;
@@ -848,8 +915,8 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
 
 // Basis vectors i0 .. i0+BLK-1 of one tier (0: TMEM, 1: shared memory, 2: L2).  Tier boundaries are multiples of
 // BLK (plan_fast), so a block never straddles two tiers; slots past the newest vector hold stale but addressable data.
-template <int EL, int BLK, int TIER>
-__device__ __forceinline__ void gs_load_block(const FastCtx<EL>& c, int i0, Vec<EL> (&vb)[BLK]) {
+template <int EL, int BLK, int TIER, int RS>
+__device__ __forceinline__ void gs_load_block(const FastCtx<EL, RS>& c, int i0, Vec<EL> (&vb)[BLK]) {
   if constexpr (TIER == 0) {
     uint32_t r[4 * EL * BLK];
     tmem_ld<4 * EL * BLK>(c.tm + 4 * EL * i0, r);
@@ -874,22 +941,26 @@ __device__ __forceinline__ void gs_load_block(const FastCtx<EL>& c, int i0, Vec<
 
 // One block: h_q = <v_{i0+q}, w> for the whole block from the same w, then w -= sum_{q < nb} h_q v_{i0+q}.
 // The coefficients are left in c.hcol[i0 .. i0+BLK).
-template <int EL, int BLK, int VARIANT>
-__device__ __forceinline__ void gs_block(const FastCtx<EL>& c, int i0, int nb, const Vec<EL> (&vb)[BLK], Vec<EL>& w) {
+template <int EL, int BLK, int VARIANT, int RS>
+__device__ __forceinline__ void gs_block(const FastCtx<EL, RS>& c, int i0, int nb, const Vec<EL> (&vb)[BLK], Vec<EL>& w) {
   double h[BLK];
 #pragma unroll
   for (int q = 0; q < BLK; ++q) h[q] = vdot_local<EL>(vb[q], w);
   if constexpr (BLK == 8 && (VARIANT & 4) != 0) block_allsum8_dmma(h, c.hcol + i0, c.lane);
   else if constexpr (BLK == 8 && (VARIANT & 2) != 0) block_allsum8_smem(h, reinterpret_cast<double*>(c.xs), c.hcol + i0, c.lane);
   else block_allsum<BLK>(h, c.hcol + i0, c.lane);
+  if constexpr (RS > 1) {
+    static_assert(BLK == 8 && (VARIANT & 4) == 0, "row-split groups: blocks of 8, coefficients published through shared memory");
+    row_combine8(c, h, c.hcol + i0);
+  }
 #pragma unroll
   for (int q = 0; q < BLK; ++q)
     if (q < nb) vaxpy(w, -h[q], vb[q]);
 }
 
 // w is orthogonalised against V[:, 0..k-1]; c.hcol[0..k-1] receives the coefficients.
-template <int EL, int BLK, int VARIANT>
-__device__ __forceinline__ void gs_orthogonalize(const FastCtx<EL>& c, int k, Vec<EL>& w) {
+template <int EL, int BLK, int VARIANT, int RS>
+__device__ __forceinline__ void gs_orthogonalize(const FastCtx<EL, RS>& c, int k, Vec<EL>& w) {
   __syncwarp();  // the gather buffer (read by the operator application) becomes the transposition buffer
   if constexpr ((VARIANT & 1) != 0) {
   // one copy of the block arithmetic for the three tiers: the hot loop has to fit the 32 KB instruction cache
@@ -926,15 +997,15 @@ __device__ __forceinline__ double transpose_partials8(const double (&p)[8], doub
   return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
-template <int EL>
-__device__ __forceinline__ void gs_load_group(const FastCtx<EL>& c, int i0, Vec<EL> (&vb)[8]) {
+template <int EL, int RS>
+__device__ __forceinline__ void gs_load_group(const FastCtx<EL, RS>& c, int i0, Vec<EL> (&vb)[8]) {
   if (i0 < c.KT) gs_load_block<EL, 8, 0>(c, i0, vb);
   else if (i0 < c.KT + c.KS) gs_load_block<EL, 8, 1>(c, i0, vb);
   else gs_load_block<EL, 8, 2>(c, i0, vb);
 }
 
-template <int EL, int SUPER>
-__device__ __forceinline__ void gs_orthogonalize_super(const FastCtx<EL>& c, int k, Vec<EL>& w) {
+template <int EL, int SUPER, int RS>
+__device__ __forceinline__ void gs_orthogonalize_super(const FastCtx<EL, RS>& c, int k, Vec<EL>& w) {
   static_assert(SUPER % 8 == 0 && SUPER >= 8, "super-block width");
   double* T = reinterpret_cast<double*>(c.xs);
   const int lane = c.lane;
@@ -1056,8 +1127,8 @@ __device__ __forceinline__ void team_apply_parts(const double2* Cpar, Vec<EL>& w
 }
 
 // main warp: orthogonalise w against V[:, 0..k-1]; coefficients in c.hcol[0..k)
-template <int EL>
-__device__ __forceinline__ void gs_team_main(const FastCtx<EL>& c, int k, Vec<EL>& w, int pending) {
+template <int EL, int RS>
+__device__ __forceinline__ void gs_team_main(const FastCtx<EL, RS>& c, int k, Vec<EL>& w, int pending) {
   const TeamView<EL> tv = team_view<EL>(c.team);
   const int lane = c.lane;
   v2_store<EL>(tv.W, w, lane);
@@ -1073,8 +1144,8 @@ __device__ __forceinline__ void gs_team_main(const FastCtx<EL>& c, int k, Vec<EL
 }
 
 // main warp: x += V[:, 0..width-1] y with y in c.g (shared memory)
-template <int EL>
-__device__ __forceinline__ void update_team_main(const FastCtx<EL>& c, int width, Vec<EL>& x, int pending) {
+template <int EL, int RS>
+__device__ __forceinline__ void update_team_main(const FastCtx<EL, RS>& c, int width, Vec<EL>& x, int pending) {
   const TeamView<EL> tv = team_view<EL>(c.team);
   const int lane = c.lane;
   if (lane == 0) { tv.cmd[0] = TEAM_CMD_UPD; tv.cmd[1] = width; tv.cmd[2] = pending; }
@@ -1094,8 +1165,8 @@ __device__ __forceinline__ void update_team_main(const FastCtx<EL>& c, int width
   }
 }
 
-template <int EL>
-__device__ __forceinline__ void basis_store_team(const FastCtx<EL>& c, int i, const Vec<EL>& a, int& pending) {
+template <int EL, int RS>
+__device__ __forceinline__ void basis_store_team(const FastCtx<EL, RS>& c, int i, const Vec<EL>& a, int& pending) {
   if (team_owner(i) == 0) { tmem_store<EL>(c.tm + 4 * EL * team_slot(i), a); }
   else { v2_store<EL>(team_view<EL>(c.team).VN, a, c.lane); pending = i; }
 }
@@ -1386,10 +1457,27 @@ __device__ __forceinline__ void qr_backsub_phase(double (&gi)[CH], const double*
   }
 }
 
+// the phases in sequence (compile-time loops: CH = 4 for one-warp columns, 4 RS for row-split groups whose restart is 2N <= 128 RS)
+template <int S0, int CH>
+struct QrRotations {
+  static __device__ __forceinline__ void run(double (&top)[CH], double* const (&colp)[CH], double* dinv, double* g, double& gcur, int width,
+                                             int nsl, int lane) {
+    qr_rotation_phase<S0, CH>(top, colp, dinv, g, gcur, width, nsl, lane);
+    if constexpr (S0 + 1 < CH) QrRotations<S0 + 1, CH>::run(top, colp, dinv, g, gcur, width, nsl, lane);
+  }
+};
+template <int S0, int CH>
+struct QrBacksubs {
+  static __device__ __forceinline__ void run(double (&gi)[CH], const double* Rg, const double* dinv, int width, int lane) {
+    qr_backsub_phase<S0, CH>(gi, Rg, dinv, width, lane);
+    if constexpr (S0 > 0) QrBacksubs<S0 - 1, CH>::run(gi, Rg, dinv, width, lane);
+  }
+};
+
 template <class CTX>
 __device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double beta) {
   const int lane = c.lane;
-  constexpr int CH = 4;  // width <= restart <= 128
+  constexpr int CH = 4 * CTX::kRS;  // width <= restart <= 128 RS
   const int nsl = (width + 31) >> 5;
   double* dinv = c.hcol;
   __syncwarp();
@@ -1402,19 +1490,13 @@ __device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double be
     top[s] = j < width ? hld(colp[s]) : 0.0;
   }
   double gcur = beta;
-  qr_rotation_phase<0, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
-  qr_rotation_phase<1, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
-  qr_rotation_phase<2, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
-  qr_rotation_phase<3, CH>(top, colp, dinv, c.g, gcur, width, nsl, lane);
+  QrRotations<0, CH>::run(top, colp, dinv, c.g, gcur, width, nsl, lane);
   __threadfence_block();
   __syncwarp();  // R (L2), dinv and g (shared memory) of all lanes are visible
   double gi[CH];
 #pragma unroll
   for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; gi[q] = i < width ? c.g[i] : 0.0; }
-  qr_backsub_phase<3, CH>(gi, c.Rg, dinv, width, lane);
-  qr_backsub_phase<2, CH>(gi, c.Rg, dinv, width, lane);
-  qr_backsub_phase<1, CH>(gi, c.Rg, dinv, width, lane);
-  qr_backsub_phase<0, CH>(gi, c.Rg, dinv, width, lane);
+  QrBacksubs<CH - 1, CH>::run(gi, c.Rg, dinv, width, lane);
   __syncwarp();
 #pragma unroll
   for (int q = 0; q < CH; ++q) { const int i = lane + 32 * q; if (i < width) c.g[i] = gi[q]; }
@@ -1422,12 +1504,12 @@ __device__ __forceinline__ void qr_solve_lean(const CTX& c, int width, double be
 }
 
 // GMRES with the blocked orthogonalisation; same interface and iteration semantics as gmres_fast_strict.
-template <int EL, int NC, int VARIANT, bool TEAM, class OP>
-__device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
+template <int EL, int NC, int VARIANT, bool TEAM, class OP, int RS>
+__device__ int gmres_fast_blocked(const FastCtx<EL, RS>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b, double tol,
                                   int restart, int maxiter) {
   int pending = -1;  // TEAM: index of a basis vector handed to its owner warp with the next command
   constexpr int BLK = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 4;
-  constexpr int CHK = 2 * EL;  // k <= restart <= 2N <= 64 EL: CHK chunks of 32 rows cover a Hessenberg column
+  constexpr int CHK = 2 * EL * RS;  // k <= restart <= 2N <= 64 EL RS: CHK chunks of 32 rows cover a Hessenberg column
   const int lane = c.lane;
   // residual estimate beta / sqrt(accum) against tol, tested as beta^2 <= tol^2 accum (no square root on the
   // critical path of an iteration; the two tests differ only when the estimate is within an ulp of tol)
@@ -1445,7 +1527,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
 #pragma unroll
       for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
       precond_fast<EL, NC>(R, v);
-      const double beta2 = warp_allsum(vdot_local<EL>(v, v));
+      const double beta2 = row_allsum(c, vdot_local<EL>(v, v));
       const double rbeta = rsqrt(beta2);
       vscale(v, rbeta);
       if constexpr (TEAM) basis_store_team<EL>(c, 0, v, pending);
@@ -1475,7 +1557,7 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
       const double nl = ok ? c.nullv[i] : 0.0;
       dpart = fma(nl, hreg[s], dpart);
     }
-    const double nrm2 = warp_allsum(vdot_local<EL>(w, w));
+    const double nrm2 = row_allsum(c, vdot_local<EL>(w, w));
     const double dsum = warp_allsum(dpart);
     // an exactly vanishing w (Krylov space exhausted, happy breakdown) gives H[k+1][k] = 0 as in the reference -- whose
     // residual estimate then drops to zero and ends the solve -- not 0 * inf
@@ -1529,23 +1611,23 @@ __device__ int gmres_fast_blocked(const FastCtx<EL>& c, const RegOps<EL, NC>& R,
   return it;
 }
 
-template <int EL, int NC, int VARIANT, bool STRICT, bool TEAM, class OP>
-__device__ __forceinline__ int gmres_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b,
+template <int EL, int NC, int VARIANT, bool STRICT, bool TEAM, class OP, int RS>
+__device__ __forceinline__ int gmres_fast(const FastCtx<EL, RS>& c, const RegOps<EL, NC>& R, const OP& op, Vec<EL>& x, const Vec<EL>& b,
                                           double tol, int restart, int maxiter) {
   if constexpr (QGD_MGS_BLOCK > 1 && !STRICT) return gmres_fast_blocked<EL, NC, VARIANT, TEAM, OP>(c, R, op, x, b, tol, restart, maxiter);
   else return gmres_fast_strict<EL, NC, OP>(c, R, op, x, b, tol, restart, maxiter);
 }
 
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, int RS = 1>
 struct FwdOpFast {  // LHSHolder (src/forward_evolution.jl:583-592)
-  const FastCtx<EL>& c; const RegOps<EL, NC>& R; const double* a_lhs;
+  const FastCtx<EL, RS>& c; const RegOps<EL, NC>& R; const double* a_lhs;
   __device__ __forceinline__ void apply(const Vec<EL>& in, Vec<EL>& out) const {
     fwd_fast<EL, M, NC, false>(c, R, in, a_lhs, out, nullptr, nullptr, nullptr);
   }
 };
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, int RS = 1>
 struct AdjOpFast {  // LHSHolderAdjoint (:624-633) through the reverse sweep
-  const FastCtx<EL>& c; const RegOps<EL, NC>& R; const double* a_lhs;
+  const FastCtx<EL, RS>& c; const RegOps<EL, NC>& R; const double* a_lhs;
   __device__ __forceinline__ void apply(const Vec<EL>& in, Vec<EL>& out) const {
     double dK[M][NC], dS[M][NC];
     adj_fast<EL, M, NC, false>(c, R, in, a_lhs, out, nullptr, dK, dS);
@@ -1595,9 +1677,31 @@ __device__ __forceinline__ void publish_segment(int* progress, int seg, int lane
   if (lane == 0) atomicExch(progress, seg + 1);
 }
 
+// the same for a row-split group: the leader draws / publishes, the group's barrier orders the slices' stores before it
+template <int EL, int RS>
+__device__ __forceinline__ size_t next_item_rs(const FastCtx<EL, RS>& c, unsigned int* counter) {
+  if constexpr (RS == 1) return next_item(counter, c.lane);
+  else {
+    if (c.slice == 0 && c.lane == 0) *c.gtick = atomicAdd(counter, 1u);
+    gsync(c);
+    const unsigned int v = *reinterpret_cast<volatile unsigned int*>(c.gtick);
+    gsync(c);  // everyone has read the word before the leader can draw again
+    return (size_t)v;
+  }
+}
+template <int EL, int RS>
+__device__ __forceinline__ void publish_segment_rs(const FastCtx<EL, RS>& c, int* progress, int seg) {
+  if constexpr (RS == 1) publish_segment(progress, seg, c.lane);
+  else {
+    __threadfence();
+    gsync(c);
+    if (c.slice == 0 && c.lane == 0) atomicExch(progress, seg + 1);
+  }
+}
+
 // control Taylor coefficients of a time level: global [2][M+1][NC] -> shared (p, q) pairs [M+1][NC]
-template <int EL, int M, int NC>
-__device__ __forceinline__ void load_cv_fast(const FastCtx<EL>& c, const double* src) {
+template <int EL, int M, int NC, int RS>
+__device__ __forceinline__ void load_cv_fast(const FastCtx<EL, RS>& c, const double* src) {
   __syncwarp();
   for (int i = c.lane; i < (M + 1) * NC; i += 32) c.cv[i] = make_double2(src[i], src[(M + 1) * NC + i]);
   __syncwarp();
@@ -1605,11 +1709,28 @@ __device__ __forceinline__ void load_cv_fast(const FastCtx<EL>& c, const double*
 
 // shared-memory carve-up: [16 bytes: TMEM address slot][warp regions]; each region = fixed part + KS basis
 // vectors (+ extra doubles)
-template <int EL, int M, int NC, bool STRICT = false, bool TEAM = false>
-__device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra,
-                                                     uint32_t tmem_base) {
-  FastCtx<EL> c;
+// doubles of shared memory per row-split group: gather buffers [2][32 EL RS] double2, partial sums [2][RS][8], ticket word
+template <int EL, int RS>
+__host__ __device__ constexpr int group_doubles() { return RS == 1 ? 0 : 2 * 2 * 32 * EL * RS + 2 * RS * 8 + 2; }
+
+template <int EL, int M, int NC, bool STRICT = false, bool TEAM = false, int RS = 1>
+__device__ __forceinline__ FastCtx<EL, RS> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra,
+                                                         uint32_t tmem_base) {
+  static_assert(RS == 1 || (!STRICT && !TEAM), "row-split groups exist for the default orthogonalisation only");
+  FastCtx<EL, RS> c;
   c.lane = threadIdx.x & 31;
+  c.slice = RS == 1 ? 0 : (int)((threadIdx.x >> 5) % RS);
+  c.bar = 1 + (int)((threadIdx.x >> 5) / RS);
+  c.vl = c.lane + 32 * EL * c.slice;
+  c.par = 0u;
+  c.gx = nullptr; c.gred = nullptr; c.gtick = nullptr;
+  if constexpr (RS > 1) {  // group regions behind the warp regions
+    double* gbase = reinterpret_cast<double*>(smem + 16) + (size_t)(blockDim.x >> 5) * a.warp_smem_doubles +
+                    (size_t)((threadIdx.x >> 5) / RS) * group_doubles<EL, RS>();
+    c.gx = reinterpret_cast<double2*>(gbase);
+    c.gred = gbase + 2 * 2 * 32 * EL * RS;
+    c.gtick = reinterpret_cast<unsigned*>(c.gred + 2 * RS * 8);
+  }
   c.N = d.N; c.N2 = d.N2; c.KS = a.ks;
   // TEAM: the four warps of the CTA serve ONE column: they share the (single) per-warp region; each owns a TMEM lane quarter
   const int warp = TEAM ? 0 : (int)(threadIdx.x >> 5);
@@ -1620,10 +1741,10 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
   c.tm = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(cols * (warp >> 2));
   if constexpr (TEAM) c.tm = tmem_base + ((uint32_t)(32 * (threadIdx.x >> 5)) << 16);
   double* w = reinterpret_cast<double*>(smem + 16) + (size_t)warp * a.warp_smem_doubles;
-  c.xs = reinterpret_cast<double2*>(w); w += FastCtx<EL>::kRingDoubles;
+  c.xs = reinterpret_cast<double2*>(w); w += FastCtx<EL, RS>::kRingDoubles;
   c.cv = reinterpret_cast<double2*>(w); w += 2 * (M + 1) * NC;
 #if QGD_COMPACT_SMEM
-  static_assert(FastCtx<EL>::kRingDoubles >= 64 * EL + 2, "g (2N + 2 doubles) aliases the gather buffer");
+  static_assert(FastCtx<EL, RS>::kRingDoubles >= 64 * EL * RS + 2, "g (2N + 2 doubles) aliases the gather buffer");
   if constexpr (STRICT) {
     c.rot = reinterpret_cast<double2*>(w); c.hcol = w; c.sub = w + d.N2 + 10; w += 2 * (d.N2 + 2 + 8);
     c.nullv = w; w += d.N2 + 2;
@@ -1655,12 +1776,13 @@ __device__ __forceinline__ FastCtx<EL> make_fast_ctx(const QgdDevProb& d, const 
 // forced solves of eval_grad_forced (a.base_history: item b is control parameter b, zero initial state, control vector 0,
 // the guard-penalty derivative accumulated on the way, no history written).
 // TEAM: the latency team above -- a CTA of four warps per column; warps 1-3 only serve the orthogonalisation.
-template <int EL, int M, int NC, bool STRICT, bool FORCED = false, bool TEAM = false>
+template <int EL, int M, int NC, bool STRICT, bool FORCED = false, bool TEAM = false, int RS = 1>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT, TEAM>(d, a, smem, &extra, tmem_base);
+  static_assert(RS == 1 || !FORCED, "forced solves of row-split problems run on the generic kernels");
+  const FastCtx<EL, RS> c = make_fast_ctx<EL, M, NC, STRICT, TEAM, RS>(d, a, smem, &extra, tmem_base);
   if constexpr (TEAM) {
     if ((threadIdx.x >> 5) > 0) {
       team_helper_loop<EL>(c.team, c.hcol, c.g, c.tm, (int)(threadIdx.x >> 5), c.lane);
@@ -1668,21 +1790,21 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
       return;
     }
   }
-  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int lane = c.lane, vl = c.vl;  // vl: row space (lane + 32 EL slice)
   const int N = d.N, N2 = d.N2;
   RegOps<EL, NC> R;
-  load_regops<EL, NC>(R, d, lane, 0);
+  load_regops<EL, NC>(R, d, vl, 0);
   double a_rhs[M + 1], a_lhs[M + 1], a_tay[M + 1];
 #pragma unroll
   for (int j = 0; j <= M; ++j) { a_rhs[j] = d.a_rhs[j]; a_lhs[j] = d.a_lhs[j]; a_tay[j] = d.a_tay[j]; }
   const size_t items = (size_t)a.B * d.ncol;
   const size_t cv_stride = (size_t)2 * (M + 1) * NC;
   const size_t slot_sz = (size_t)N2 * (M + 1);
-  const FwdOpFast<EL, M, NC> op{c, R, a_lhs};
+  const FwdOpFast<EL, M, NC, RS> op{c, R, a_lhs};
   // columns need different numbers of GMRES iterations: warps draw (segment, control vector, column) tickets
   const int S = a.seg_steps, nseg = (d.nsteps + S - 1) / S;
   const size_t tickets = items * (size_t)nseg;
-  for (size_t ticket = next_item(a.work_counter, lane); ticket < tickets; ticket = next_item(a.work_counter, lane)) {
+  for (size_t ticket = next_item_rs(c, a.work_counter); ticket < tickets; ticket = next_item_rs(c, a.work_counter)) {
     const int seg = (int)(ticket / items);
     const size_t item = ticket % items;
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
@@ -1719,13 +1841,13 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
     if (seg == 0) {
 #pragma unroll
       for (int e = 0; e < EL; ++e) {
-        const int r = lane + 32 * e;
+        const int r = vl + 32 * e;
         x.u[e] = (r < N && !gradf) ? d.u0[r + (size_t)N * col] : 0.0;
         x.v[e] = (r < N && !gradf) ? d.v0[r + (size_t)N * col] : 0.0;
       }
     } else {
       wait_segment(a.progress + item, seg, lane, a.err);
-      vload_cg(x, carry, N, lane);
+      vload_cg(x, carry, N, vl);
     }
     load_cv_fast<EL, M, NC>(c, cvb + (size_t)n0 * cv_stride);
     const int nend = last ? n1 : n1 - 1;  // the last segment also forms the Taylor columns at the final time (forward_evolution.jl:232-242)
@@ -1756,7 +1878,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
       const int it = gmres_fast<EL, NC, QGD_FWD_VARIANT, STRICT, TEAM>(c, R, op, x, rhs, d.abstol, N2, N2);
       if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
     }
-    vstore(x, carry, N, lane);
+    vstore(x, carry, N, vl);
     if constexpr (FORCED) {
       if (gradf) {  // guard-penalty derivative partial of this segment; the sum is carried in guardcol across segments
         const double g = warp_allsum(gpen) * (d.dt / d.tf);
@@ -1764,7 +1886,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
         if (lane == 0) *gc = (seg == 0 ? 0.0 : __ldcg(gc)) + g;
       }
     }
-    publish_segment(a.progress + item, seg, lane);
+    publish_segment_rs(c, a.progress + item, seg);
   }
   if constexpr (TEAM) {  // release the helper warps
     if (lane == 0) team_view<EL>(c.team).cmd[0] = TEAM_CMD_EXIT;
@@ -1777,8 +1899,8 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
 // the reduced inner products g^K, g^S [M][NC] of that time level (left in gKs / gSs, shared memory).  It runs twice per
 // time step; inlining it twice costs 21 KB of instruction cache in a kernel whose GMRES loop has to stay resident, and
 // rolling the two calls into a loop spills registers into that loop.
-template <int EL, int M, int NC>
-__device__ __noinline__ void grad_side_fast(const FastCtx<EL>& c, const RegOps<EL, NC>& R, const Vec<EL>& lam, const double* alpha_src,
+template <int EL, int M, int NC, int RS>
+__device__ __noinline__ void grad_side_fast(const FastCtx<EL, RS>& c, const RegOps<EL, NC>& R, const Vec<EL>& lam, const double* alpha_src,
                                             double sign, Vec<EL>& out, const double* hist, bool last_use, double* gKs, double* gSs) {
   double gK[M][NC], gS[M][NC], alpha[M + 1];
 #pragma unroll
@@ -1800,13 +1922,13 @@ __device__ __noinline__ void grad_side_fast(const FastCtx<EL>& c, const RegOps<E
 
 // grad_acc[theta] -= sum_r table_p[r][theta] gK[r][k(theta)] + table_q[r][theta] gS[r][k(theta)]
 template <int M, int NC>
-__device__ __forceinline__ void accumulate_grad_fast(int lane, int P, const QgdDevControl* ctrls, const double* table_n,
+__device__ __forceinline__ void accumulate_grad_fast(int t0, int tstep, int P, const QgdDevControl* ctrls, const double* table_n,
                                                      const double* gKs, const double* gSs, double* gacc) {
   const int nd = M + 1;
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
     const int off = ctrls[k].offset, nco = ctrls[k].ncoeff;
-    for (int t = lane; t < nco; t += 32) {
+    for (int t = t0; t < nco; t += tstep) {  // a row-split group deals the parameters over its warps
       double s = 0.0;
 #pragma unroll
       for (int r = 0; r < M; ++r) {
@@ -1825,13 +1947,13 @@ __device__ __forceinline__ void accumulate_grad_fast(int lane, int P, const QgdD
   }
 }
 
-template <int EL, int M, int NC, bool STRICT, bool TEAM = false>
+template <int EL, int M, int NC, bool STRICT, bool TEAM = false, int RS = 1>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a,
                                                                                const QgdDevControl* __restrict__ ctrls) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, STRICT, TEAM>(d, a, smem, &extra, tmem_base);
+  const FastCtx<EL, RS> c = make_fast_ctx<EL, M, NC, STRICT, TEAM, RS>(d, a, smem, &extra, tmem_base);
   if constexpr (TEAM) {
     if ((threadIdx.x >> 5) > 0) {
       team_helper_loop<EL>(c.team, c.hcol, c.g, c.tm, (int)(threadIdx.x >> 5), c.lane);
@@ -1839,10 +1961,10 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       return;
     }
   }
-  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const int lane = c.lane, vl = c.vl;  // vl: row space (lane + 32 EL slice)
   const int N = d.N, N2 = d.N2, Nt = d.nsteps + 1, P = d.P;
   RegOps<EL, NC> R0;
-  load_regops<EL, NC>(R0, d, lane, 1);
+  load_regops<EL, NC>(R0, d, vl, 1);
   const RegOps<EL, NC> R = R0;  // const object: the non-inlined callee cannot legally change it
   double a_rhs[M + 1], a_lhs[M + 1], a_imp[M + 1];
 #pragma unroll
@@ -1854,7 +1976,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
 #if QGD_COMPACT_SMEM
   // reduced g^K, g^S [M][NC] each: in the gather buffer (idle between the gradient sweep and the contraction with the
   // control basis table); the gradient partial itself accumulates in L2 (gcol), touched once per time step
-  static_assert(FastCtx<EL>::kRingDoubles >= 2 * M * NC, "gKs / gSs alias the gather buffer");
+  static_assert(FastCtx<EL, RS>::kRingDoubles >= 2 * M * NC, "gKs / gSs alias the gather buffer");
   double* gKs = reinterpret_cast<double*>(c.xs);
   double* gSs = gKs + M * NC;
   (void)extra;
@@ -1863,11 +1985,11 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
   double* gKs = gacc + P;        // [M][NC] reduced g^K
   double* gSs = gKs + M * NC;    // [M][NC] reduced g^S
 #endif
-  const AdjOpFast<EL, M, NC> op{c, R, a_lhs};
+  const AdjOpFast<EL, M, NC, RS> op{c, R, a_lhs};
   const double fsc = -2.0 * d.dt / d.tf;
   const int S = a.seg_steps, nseg = (d.nsteps + S - 1) / S;
   const size_t tickets = items * (size_t)nseg;
-  for (size_t ticket = next_item(a.work_counter, lane); ticket < tickets; ticket = next_item(a.work_counter, lane)) {
+  for (size_t ticket = next_item_rs(c, a.work_counter); ticket < tickets; ticket = next_item_rs(c, a.work_counter)) {
     const int seg = (int)(ticket / items);
     const size_t item = ticket % items;
     const int b = (int)(item / d.ncol), cl = (int)(item % d.ncol), col = d.col0 + cl;
@@ -1883,14 +2005,14 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
 #endif
     if (seg == 0) {
       for (int t = lane; t < P; t += 32) gacc[t] = 0.0;
-      vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
-      if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, lane);
+      vload(lam, a.terminal + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, vl);
+      if (lam0) vstore(lam, lam0 + (size_t)N2 * d.nsteps, N, vl);
     } else {
       wait_segment(a.progress + item, seg, lane, a.err);
 #if !QGD_COMPACT_SMEM
       for (int t = lane; t < P; t += 32) gacc[t] = __ldcg(gcol + t);
 #endif
-      vload_cg(lam, carry, N, lane);
+      vload_cg(lam, carry, N, vl);
     }
     load_cv_fast<EL, M, NC>(c, cvb + (size_t)(n_hi + 1) * cv_stride);
     for (int n = n_hi; n >= n_lo; --n) {
@@ -1898,12 +2020,12 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
 #if QGD_BWD_MERGE_SIDES == 2
       // implicit side: time level n+1 (its control values are the ones currently loaded), coefficients -a_lhs
       grad_side_fast<EL, M, NC>(c, R, lam, d.a_lhs, -1.0, w0, hist + slot_sz * (n + 1), true, gKs, gSs);
-      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)(n + 1) * tab_stride, gKs, gSs, gacc);
+      accumulate_grad_fast<M, NC>(lane + 32 * c.slice, 32 * RS, P, ctrls, d.table + (size_t)(n + 1) * tab_stride, gKs, gSs, gacc);
       __syncwarp();
       // explicit side: time level n, coefficients a_rhs; rhs = R(t_n)^T lambda_{n+1}
       load_cv_fast<EL, M, NC>(c, cvb + (size_t)n * cv_stride);
       grad_side_fast<EL, M, NC>(c, R, lam, d.a_rhs, 1.0, rhs, hist + slot_sz * n, false, gKs, gSs);
-      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
+      accumulate_grad_fast<M, NC>(lane + 32 * c.slice, 32 * RS, P, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
       __syncwarp();
 #elif !QGD_BWD_MERGE_SIDES
       {
@@ -1918,11 +2040,11 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       for (int r = 0; r < M; ++r)
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
-          const double sK = warp_allsum(gK[r][k]), sS = warp_allsum(gS[r][k]);
+          const double sK = row_allsum(c, gK[r][k]), sS = row_allsum(c, gS[r][k]);
           if (lane == 0) { gKs[r * NC + k] = sK; gSs[r * NC + k] = sS; }
         }
       __syncwarp();
-      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)(n + 1) * tab_stride, gKs, gSs, gacc);
+      accumulate_grad_fast<M, NC>(lane + 32 * c.slice, 32 * RS, P, ctrls, d.table + (size_t)(n + 1) * tab_stride, gKs, gSs, gacc);
       __syncwarp();
       // ---- explicit side: time level n
       load_cv_fast<EL, M, NC>(c, cvb + (size_t)n * cv_stride);
@@ -1935,11 +2057,11 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
       for (int r = 0; r < M; ++r)
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
-          const double sK = warp_allsum(gK[r][k]), sS = warp_allsum(gS[r][k]);
+          const double sK = row_allsum(c, gK[r][k]), sS = row_allsum(c, gS[r][k]);
           if (lane == 0) { gKs[r * NC + k] = sK; gSs[r * NC + k] = sS; }
         }
       __syncwarp();
-      accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
+      accumulate_grad_fast<M, NC>(lane + 32 * c.slice, 32 * RS, P, ctrls, d.table + (size_t)n * tab_stride, gKs, gSs, gacc);
       __syncwarp();
       }
 #else
@@ -1962,17 +2084,17 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
         for (int r = 0; r < M; ++r)
 #pragma unroll
           for (int k = 0; k < NC; ++k) {
-            const double sK = warp_allsum(gK[r][k]), sS = warp_allsum(gS[r][k]);
+            const double sK = row_allsum(c, gK[r][k]), sS = row_allsum(c, gS[r][k]);
             if (lane == 0) { gKs[r * NC + k] = sK; gSs[r * NC + k] = sS; }
           }
         __syncwarp();
-        accumulate_grad_fast<M, NC>(lane, P, ctrls, d.table + (size_t)lvl * tab_stride, gKs, gSs, gacc);
+        accumulate_grad_fast<M, NC>(lane + 32 * c.slice, 32 * RS, P, ctrls, d.table + (size_t)lvl * tab_stride, gKs, gSs, gacc);
         __syncwarp();
       }
 #endif
       if (n >= 1) {
         // guard forcing f_n = -(2 dt/tf) W w_n (interior point: trapezoid weight 1), W diagonal
-        vload_cg(w0, hist + slot_sz * n, N, lane);
+        vload_cg(w0, hist + slot_sz * n, N, vl);
 #pragma unroll
         for (int e = 0; e < EL; ++e) {
           rhs.u[e] = fma(fsc, R.wu[e] * w0.u[e], rhs.u[e]);
@@ -1980,7 +2102,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
         }
         // x0 = lambda_{n+1} (forward_evolution.jl:450)
         const int it = gmres_fast<EL, NC, QGD_BWD_VARIANT, STRICT, TEAM>(c, R, op, lam, rhs, d.abstol, N2, N2);
-        if (lam0) vstore(lam, lam0 + (size_t)N2 * n, N, lane);
+        if (lam0) vstore(lam, lam0 + (size_t)N2 * n, N, vl);
         if (a.iters && lane == 0) a.iters[(size_t)n + (size_t)d.nsteps * ((size_t)cl + (size_t)d.ncol * b)] = it;
       }
     }
@@ -1988,8 +2110,8 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
 #if !QGD_COMPACT_SMEM
     for (int t = lane; t < P; t += 32) gcol[t] = gacc[t];
 #endif
-    if (seg < nseg - 1) vstore(lam, carry, N, lane);
-    publish_segment(a.progress + item, seg, lane);
+    if (seg < nseg - 1) vstore(lam, carry, N, vl);
+    publish_segment_rs(c, a.progress + item, seg);
   }
   if constexpr (TEAM) {  // release the helper warps
     if (lane == 0) team_view<EL>(c.team).cmd[0] = TEAM_CMD_EXIT;

@@ -15,12 +15,15 @@ struct FastCfg { int grid, threads, wpc, ks, kt, tmem_cols, warp_doubles, h_smem
 // One CTA per SM, all of its shared memory split between the warps; whatever is left after the fixed
 // per-warp arrays holds the resident part of the Krylov basis.
 template <class K>
-FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t items, int extra_doubles, int restart) {
+FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t items, int extra_doubles, int restart, int rs = 1,
+                  int group_dbl = 0) {
   const size_t max_smem = h->prop.sharedMemPerBlockOptin;
   const int sms = h->prop.multiProcessorCount;
   FastCfg L{};
-  L.wpc = (int)std::min<size_t>(QGD_WARPS_PER_CTA, std::max<size_t>(1, (items + sms - 1) / sms));
-  if (h->opt[QGD_OPT_LATENCY_WARPS] > 0) L.wpc = (int)h->opt[QGD_OPT_LATENCY_WARPS];
+  // rs > 1 (row-split groups): an item takes rs warps of a CTA
+  L.wpc = rs * (int)std::min<size_t>(QGD_WARPS_PER_CTA / rs, std::max<size_t>(1, (items + sms - 1) / sms));
+  if (h->opt[QGD_OPT_LATENCY_WARPS] > 0 && rs == 1) L.wpc = (int)h->opt[QGD_OPT_LATENCY_WARPS];
+  const int ngroups = rs > 1 ? L.wpc / rs : 0;
   const int vec = 2 * 32 * el;
   const int base = (fixed_doubles + extra_doubles + 1) & ~1;
   // tensor-memory tier: warps w and w + 4 of a CTA share a lane quarter, so each gets 512 / groups columns;
@@ -36,7 +39,7 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   }
   constexpr int blk = QGD_MGS_BLOCK > 1 ? QGD_MGS_BLOCK : 1;  // a Gram-Schmidt block never straddles two tiers
   L.kt = (L.kt / blk) * blk;
-  const long per_warp = (long)((max_smem - 16) / 8 / L.wpc) & ~1L;
+  const long per_warp = (long)(((max_smem - 16) / 8 - (size_t)ngroups * group_dbl) / L.wpc) & ~1L;
   // Few columns in flight (one or two warps per SM -- a single gradient evaluation, what optimize_gate asks for): the
   // packed Hessenberg matrix of the warp fits into shared memory beside the whole Krylov basis, so the end-of-solve
   // least squares reads shared memory instead of waiting an L2 round trip per rotation.
@@ -53,9 +56,10 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   ks = L.ks;
   L.warp_doubles = base + (int)ks * vec + L.h_smem;
   L.threads = 32 * L.wpc;
-  L.smem = 16 + (size_t)L.wpc * L.warp_doubles * 8;
+  L.smem = 16 + ((size_t)L.wpc * L.warp_doubles + (size_t)ngroups * group_dbl) * 8;
   CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-  const size_t ctas = (items + L.wpc - 1) / L.wpc;
+  const size_t per_cta = (size_t)(L.wpc / rs);
+  const size_t ctas = (items + per_cta - 1) / per_cta;
   L.grid = (int)std::max<size_t>(1, std::min<size_t>(ctas, (size_t)sms));
   return L;
 }
@@ -153,6 +157,21 @@ void launch_backward_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   ensure_krylov_fast(h, L, EL, d.N2, a);
   launch_sweep(h, k_backward_fast<EL, M, NC, STRICT>, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
 }
+// Row-split groups (qgd_fast.cuh, FastCtx RS): sparse problems with 64 < N <= 128 (two warps per column) and 128 < N <= 256 (four)
+template <int M, int NC, int RS>
+void launch_forward_fast_rs_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  auto kernel = k_forward_fast<2, M, NC, false, false, false, RS>;
+  FastCfg L = plan_fast(h, kernel, fast_fixed_doubles<2, M, NC, false, RS>(d.N2), 2, (size_t)a.B * d.ncol, 0, d.N2, RS, group_doubles<2, RS>());
+  ensure_krylov_fast(h, L, 2, d.N2, a);
+  launch_sweep(h, kernel, L, d, a);
+}
+template <int M, int NC, int RS>
+void launch_backward_fast_rs_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  auto kernel = k_backward_fast<2, M, NC, false, false, RS>;
+  FastCfg L = plan_fast(h, kernel, fast_fixed_doubles<2, M, NC, false, RS>(d.N2), 2, (size_t)a.B * d.ncol, 0, d.N2, RS, group_doubles<2, RS>());
+  ensure_krylov_fast(h, L, 2, d.N2, a);
+  launch_sweep(h, kernel, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
+}
 template <int EL, int M, int NC>
 void launch_terminal_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   const int restart = std::min(20, d.N2);
@@ -225,6 +244,18 @@ void launch_backward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
 #define QGD_DEFINE_FAST_LAUNCHERS_FORCED(M)                                                                                 \
   bool launch_forward_fast_forced_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc) {                       \
     QGD_FAST_SHAPES(QGD_FAST_CASE_FWD_F, M) return false;                                                                   \
+  }
+
+// Row-split groups in translation units of their own: (RS, NC) in {2, 4} x {2, 3}.
+#define QGD_FAST_CASE_RS(WHICH, M, NC, RS) if (rs == RS && nc == NC) { launch_##WHICH##_fast_rs_t<M, NC, RS>(h, d, a); return true; }
+#define QGD_DEFINE_FAST_LAUNCHERS_RS(M)                                                                                     \
+  bool launch_forward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                           \
+    QGD_FAST_CASE_RS(forward, M, 2, 2) QGD_FAST_CASE_RS(forward, M, 3, 2) QGD_FAST_CASE_RS(forward, M, 2, 4)                  \
+    QGD_FAST_CASE_RS(forward, M, 3, 4) return false;                                                                        \
+  }                                                                                                                         \
+  bool launch_backward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                          \
+    QGD_FAST_CASE_RS(backward, M, 2, 2) QGD_FAST_CASE_RS(backward, M, 3, 2) QGD_FAST_CASE_RS(backward, M, 2, 4)               \
+    QGD_FAST_CASE_RS(backward, M, 3, 4) return false;                                                                       \
   }
 
 // The latency team (four warps per column) in translation units of its own.

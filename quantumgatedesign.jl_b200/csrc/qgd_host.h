@@ -77,6 +77,7 @@ struct qgd_handle {
   // register-operator fast path (qgd_fast.cuh): structure test done once at creation
   bool fast_ok = false;
   int fast_el = 0;
+  int fast_rs = 1;  // warps per column: 1 (N <= 64), 2 (N <= 128), 4 (N <= 256) -- row-split groups of qgd_fast.cuh
   // dense tensor-core path (qgd_dense.cu): row-major dense copies of the operators [(Nc+1)][2][N][N] (operator 0 = drift)
   std::vector<double> dense_ops;
   DevBuf d_dense, d_comb, d_dense_ws;
@@ -141,7 +142,9 @@ QGD_DECLARE_LAUNCHERS(8)
   bool launch_backward_fast_strict_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);             \
   bool launch_forward_fast_forced_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);              \
   bool launch_forward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);                \
-  bool launch_backward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);
+  bool launch_backward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);               \
+  bool launch_forward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc);                  \
+  bool launch_backward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc);
 QGD_DECLARE_FAST_LAUNCHERS(1)
 QGD_DECLARE_FAST_LAUNCHERS(2)
 QGD_DECLARE_FAST_LAUNCHERS(3)
