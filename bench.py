@@ -296,9 +296,35 @@ def extras_single_gpu(q, h, args, prob, controls, tgt, target, order, P, local):
                             "(about 63 GMRES iterations per step), 592 control vectors x 8 columns x 550 steps", "kernel_ms": ms,
                 "column_steps_per_s": 592 * 8 * 550 / (ms * 1e-3)}
 
+    def mid():
+        # not a BASELINE configuration: the sparse mid-size family (64 < N <= 256) on the row-split register-operator sweeps,
+        # with the generic row-ELL kernels that served it before timed beside them
+        freqs, kerr = q.configs.cnot3_physics()
+        sizes, nst, nb = (5, 5, 5), 60, 74
+        pm = q.DispersiveProblem(sizes, (2, 2, 2), freqs, freqs, kerr, float(nst), nst, sparse_rep=True, gmres_abstol=1e-12, gmres_reltol=1e-12,
+                                 preconditioner_type=q.DiagonalHamiltonianPreconditioner)
+        cm = [q.CarrierControl(q.BSpline2Control(10, float(nst)), [0.0, -kerr[k, (k + 1) % 3]]) for k in range(3)]
+        pcs = pcof_batch(q, q.get_number_of_control_parameters(cm), nb, 0)
+        tm = q.complex_to_real(q.create_initial_conditions(sizes, (2, 2, 2)))
+        hm = q.Handle(pm, cm, device=local)
+        res = {}
+        for name, off in (("row_split_groups", 0), ("generic_kernels", 1)):
+            hm.set_option(q.backend.OPT_DISABLE_FAST, off)
+            for _ in range(2):
+                out = hm.discrete_adjoint(pcs, tm, order=8)
+            st = hm.stats()
+            res[name] = {"forward_ms": st["last_forward_ms"], "adjoint_ms": st["last_backward_ms"], "device_total_ms": st["last_total_ms"],
+                         "evals_per_s": nb / (st["last_total_ms"] * 1e-3)}
+            res[name + "_grad"] = out["grad"]
+        g1, g0 = res.pop("row_split_groups_grad"), res.pop("generic_kernels_grad")
+        hm.close()
+        return {"workload": "sparse dispersive (5,5,5) levels N=125 nic=8 Nc=3 order 8 nsteps=60 tol 1e-12, 74 control vectors (two warps per column)",
+                **res, "grad_rel_diff": float(np.abs(g1 - g0).max() / np.abs(g0).max())}
+
     guarded("c1", c1)
     guarded("c3", c3)
     guarded("c5", c5)
+    guarded("mid_size_n125", mid)
     return ex
 
 

@@ -188,8 +188,8 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
   h->stats.kernel_launches++;
 }
 
-// (EL, NC) shapes built for every M: N <= 32 with 1..3 control operators, N <= 64 with 2..3.
-#define QGD_FAST_SHAPES(X, M) X(1, M, 1) X(1, M, 2) X(1, M, 3) X(2, M, 2) X(2, M, 3)
+// (EL, NC) shapes built for every M: N <= 32 with 1..4 control operators (four two-level qubits: N = 16), N <= 64 with 2..3.
+#define QGD_FAST_SHAPES(X, M) X(1, M, 1) X(1, M, 2) X(1, M, 3) X(1, M, 4) X(2, M, 2) X(2, M, 3)
 
 }  // namespace
 
@@ -246,16 +246,16 @@ void launch_backward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
     QGD_FAST_SHAPES(QGD_FAST_CASE_FWD_F, M) return false;                                                                   \
   }
 
-// Row-split groups in translation units of their own: (RS, NC) in {2, 4} x {2, 3}.
+// Row-split groups in translation units of their own: (RS, NC) in {2, 4} x {2, 3, 4}.
 #define QGD_FAST_CASE_RS(WHICH, M, NC, RS) if (rs == RS && nc == NC) { launch_##WHICH##_fast_rs_t<M, NC, RS>(h, d, a); return true; }
 #define QGD_DEFINE_FAST_LAUNCHERS_RS(M)                                                                                     \
   bool launch_forward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                           \
     QGD_FAST_CASE_RS(forward, M, 2, 2) QGD_FAST_CASE_RS(forward, M, 3, 2) QGD_FAST_CASE_RS(forward, M, 2, 4)                  \
-    QGD_FAST_CASE_RS(forward, M, 3, 4) return false;                                                                        \
+    QGD_FAST_CASE_RS(forward, M, 3, 4) QGD_FAST_CASE_RS(forward, M, 4, 2) QGD_FAST_CASE_RS(forward, M, 4, 4) return false;                                                                        \
   }                                                                                                                         \
   bool launch_backward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                          \
     QGD_FAST_CASE_RS(backward, M, 2, 2) QGD_FAST_CASE_RS(backward, M, 3, 2) QGD_FAST_CASE_RS(backward, M, 2, 4)               \
-    QGD_FAST_CASE_RS(backward, M, 3, 4) return false;                                                                       \
+    QGD_FAST_CASE_RS(backward, M, 3, 4) QGD_FAST_CASE_RS(backward, M, 4, 2) QGD_FAST_CASE_RS(backward, M, 4, 4) return false;                                                                       \
   }
 
 // The latency team (four warps per column) in translation units of its own.
