@@ -597,9 +597,10 @@ bool try_backward_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
 // terminal condition on the register operators (default orthogonalisation only: the strict option keeps the generic kernel,
 // whose Gram-Schmidt is the reference's one projection at a time)
 bool try_terminal_fast(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {
-  if (!fast_applicable(h, d.m) || h->opt[QGD_OPT_STRICT_MGS] || h->fast_rs > 1) return false;
+  if (!fast_applicable(h, d.m) || h->opt[QGD_OPT_STRICT_MGS]) return false;
   const int64_t sweeps = h->stats.fast_path_launches;  // that counter is for the two sweep kernels
-  const bool done = [&]() -> bool { QGD_FAST_SWITCH(d.m, launch_terminal_fast, h, d, a, h->fast_el, h->Nc) }();
+  const bool done = h->fast_rs > 1 ? [&]() -> bool { QGD_FAST_SWITCH(d.m, launch_terminal_fast_rs, h, d, a, h->fast_rs, h->Nc) }()
+                                   : [&]() -> bool { QGD_FAST_SWITCH(d.m, launch_terminal_fast, h, d, a, h->fast_el, h->Nc) }();
   h->stats.fast_path_launches = sweeps;
   return done;
 }

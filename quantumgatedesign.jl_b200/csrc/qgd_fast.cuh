@@ -282,6 +282,44 @@ __device__ __forceinline__ void row_combine8(const FastCtx<EL, RS>& c, double (&
   }
 }
 
+// block_allsum8_smem for a row-split group in one go: the warp's totals leave the tensor-core reduction straight into the
+// group's slot (no round trip through the warp's own Hessenberg column first), one barrier, every warp sums the RS slices.
+#ifndef QGD_RS_FUSED_RED
+#define QGD_RS_FUSED_RED 1
+#endif
+template <int EL, int RS>
+__device__ __forceinline__ void block_allsum8_group(const FastCtx<EL, RS>& c, double (&p)[8], double* T, double* slot) {
+  const int lane = c.lane;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) T[32 * q + (lane ^ (4 * (q & 3)))] = p[q];
+  __syncwarp();
+  const int qv = lane >> 2, s = lane & 3;
+  const double* row = T + 32 * qv + s;
+  const int sw = qv & 3;
+  double a[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) a[t] = row[4 * (t ^ sw)];
+  const double r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  double c0, c1;
+  dmma884(c0, c1, 1.0, r);
+  double* buf = c.gred + (c.par & 1u) * (RS * 8);
+  c.par ^= 1u;
+  if (lane < 4) reinterpret_cast<double2*>(buf + c.slice * 8)[lane] = make_double2(c0, c1);  // totals of values 2 lane, 2 lane + 1
+  gsync(c);
+#pragma unroll
+  for (int q = 0; q < 8; q += 2) {
+    double2 t = reinterpret_cast<const double2*>(buf)[q >> 1];
+#pragma unroll
+    for (int sl = 1; sl < RS; ++sl) {
+      const double2 u = reinterpret_cast<const double2*>(buf + sl * 8)[q >> 1];
+      t.x += u.x; t.y += u.y;
+    }
+    p[q] = t.x; p[q + 1] = t.y;
+    if (lane == (q >> 1)) reinterpret_cast<double2*>(slot)[q >> 1] = t;
+  }
+  __syncwarp();
+}
+
 // z-sums of one vector (in the gather buffer): K_k x and S_k x restricted to this lane's rows.
 template <int EL, int NC>
 struct ZS { double Ku[EL][NC], Kv[EL][NC], Su[EL][NC], Sv[EL][NC]; };
@@ -657,10 +695,10 @@ __device__ __forceinline__ void trsv_fast(const FastCtx<EL, RS>& c, int width) {
 
 // One modified Gram-Schmidt step against basis vector i (already in registers) fused with the progressive
 // Givens update of the Hessenberg column: branch free; nul = nullv[i], rt = rot[i] (rot[0] = identity).
-template <int EL>
-__device__ __forceinline__ void mgs_step(int i, const Vec<EL>& vi, Vec<EL>& w, double& dsum, double& hprev, double* rcol, double nul,
-                                         double2 rt) {
-  const double h = warp_allsum(vdot_local<EL>(vi, w));
+template <int EL, int RS>
+__device__ __forceinline__ void mgs_step(const FastCtx<EL, RS>& c, int i, const Vec<EL>& vi, Vec<EL>& w, double& dsum, double& hprev, double* rcol,
+                                         double nul, double2 rt) {
+  const double h = row_allsum(c, vdot_local<EL>(vi, w));
   vaxpy(w, -h, vi);
   dsum = fma(nul, h, dsum);
   const double r = rt.x * hprev + rt.y * h;  // row i-1 of R, final after rotation i-1
@@ -679,7 +717,7 @@ __device__ int gmres_fast_strict(const FastCtx<EL, RS>& c, const RegOps<EL, NC>&
 #pragma unroll
   for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
   precond_fast<EL, NC>(R, v);
-  double beta2 = warp_allsum(vdot_local<EL>(v, v));
+  double beta2 = row_allsum(c, vdot_local<EL>(v, v));
   double rbeta = rsqrt(beta2), beta = beta2 * rbeta;
   // reltol >= 0 (terminal-condition solves, gmres! driver): tol = max(reltol * ||initial residual||, tol) as IterativeSolvers
   // sets it; the time-stepping solves pass -1 (fixed absolute tolerance)
@@ -711,7 +749,7 @@ __device__ int gmres_fast_strict(const FastCtx<EL, RS>& c, const RegOps<EL, NC>&
         tmem_load_issue<EL>(c.tm + 4 * EL * inext, rn);
         const double nul_n = c.nullv[i + 1];
         const double2 rt_n = c.rot[i + 1];
-        mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
+        mgs_step<EL>(c, i, vi, w, dsum, hprev, rcol, nul, rt);
         tmem_wait_ld();
         tmem_unpack<EL>(rn, vi);
         nul = nul_n; rt = rt_n;
@@ -727,7 +765,7 @@ __device__ int gmres_fast_strict(const FastCtx<EL, RS>& c, const RegOps<EL, NC>&
         v2_load<EL>(vn, c.Vs + (size_t)inext * 32 * EL, lane);
         const double nul_n = c.nullv[i + 1];
         const double2 rt_n = c.rot[i + 1];
-        mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
+        mgs_step<EL>(c, i, vi, w, dsum, hprev, rcol, nul, rt);
         vi = vn; nul = nul_n; rt = rt_n;
       }
     }
@@ -742,11 +780,11 @@ __device__ int gmres_fast_strict(const FastCtx<EL, RS>& c, const RegOps<EL, NC>&
         v2_load_cg<EL>(vnn, base + (size_t)min(i + 2, k - 1) * 32 * EL, lane);
         const double nul_n = c.nullv[i + 1];
         const double2 rt_n = c.rot[i + 1];
-        mgs_step<EL>(i, vi, w, dsum, hprev, rcol, nul, rt);
+        mgs_step<EL>(c, i, vi, w, dsum, hprev, rcol, nul, rt);
         vi = vn; vn = vnn; nul = nul_n; rt = rt_n;
       }
     }
-    const double nrm2 = warp_allsum(vdot_local<EL>(w, w));
+    const double nrm2 = row_allsum(c, vdot_local<EL>(w, w));
     // 1/||w|| and ||w|| from one reciprocal square root; an exactly vanishing w (the Krylov space is exhausted: happy
     // breakdown) gives H[k+1][k] = 0 as in the reference (its estimate then drops to zero and the solve ends), not 0 * inf
     const double rnrm = rsqrt(nrm2), nrm = nrm2 > 0.0 ? nrm2 * rnrm : 0.0;
@@ -787,7 +825,7 @@ __device__ int gmres_fast_strict(const FastCtx<EL, RS>& c, const RegOps<EL, NC>&
 #pragma unroll
         for (int e = 0; e < EL; ++e) { v.u[e] = b.u[e] - w.u[e]; v.v[e] = b.v[e] - w.v[e]; }
         precond_fast<EL, NC>(R, v);
-        beta2 = warp_allsum(vdot_local<EL>(v, v));
+        beta2 = row_allsum(c, vdot_local<EL>(v, v));
         rbeta = rsqrt(beta2); beta = beta2 * rbeta;
         vscale(v, rbeta);
         basis_store<EL>(c, 0, v);
@@ -946,12 +984,16 @@ __device__ __forceinline__ void gs_block(const FastCtx<EL, RS>& c, int i0, int n
   double h[BLK];
 #pragma unroll
   for (int q = 0; q < BLK; ++q) h[q] = vdot_local<EL>(vb[q], w);
-  if constexpr (BLK == 8 && (VARIANT & 4) != 0) block_allsum8_dmma(h, c.hcol + i0, c.lane);
-  else if constexpr (BLK == 8 && (VARIANT & 2) != 0) block_allsum8_smem(h, reinterpret_cast<double*>(c.xs), c.hcol + i0, c.lane);
-  else block_allsum<BLK>(h, c.hcol + i0, c.lane);
-  if constexpr (RS > 1) {
-    static_assert(BLK == 8 && (VARIANT & 4) == 0, "row-split groups: blocks of 8, coefficients published through shared memory");
-    row_combine8(c, h, c.hcol + i0);
+  if constexpr (RS > 1 && QGD_RS_FUSED_RED && BLK == 8 && (VARIANT & 6) == 2) {
+    block_allsum8_group(c, h, reinterpret_cast<double*>(c.xs), c.hcol + i0);
+  } else {
+    if constexpr (BLK == 8 && (VARIANT & 4) != 0) block_allsum8_dmma(h, c.hcol + i0, c.lane);
+    else if constexpr (BLK == 8 && (VARIANT & 2) != 0) block_allsum8_smem(h, reinterpret_cast<double*>(c.xs), c.hcol + i0, c.lane);
+    else block_allsum<BLK>(h, c.hcol + i0, c.lane);
+    if constexpr (RS > 1) {
+      static_assert(BLK == 8 && (VARIANT & 4) == 0, "row-split groups: blocks of 8, coefficients published through shared memory");
+      row_combine8(c, h, c.hcol + i0);
+    }
   }
 #pragma unroll
   for (int q = 0; q < BLK; ++q)
@@ -1716,7 +1758,7 @@ __host__ __device__ constexpr int group_doubles() { return RS == 1 ? 0 : 2 * 2 *
 template <int EL, int M, int NC, bool STRICT = false, bool TEAM = false, int RS = 1>
 __device__ __forceinline__ FastCtx<EL, RS> make_fast_ctx(const QgdDevProb& d, const SweepArgs& a, unsigned char* smem, double** extra,
                                                          uint32_t tmem_base) {
-  static_assert(RS == 1 || (!STRICT && !TEAM), "row-split groups exist for the default orthogonalisation only");
+  static_assert(RS == 1 || !TEAM, "a row-split group is not a latency team");
   FastCtx<EL, RS> c;
   c.lane = threadIdx.x & 31;
   c.slice = RS == 1 ? 0 : (int)((threadIdx.x >> 5) % RS);
@@ -2128,25 +2170,25 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_backward_fast(con
 // at 64 levels and tolerances of 1e-12 and below it runs into its 2N-iteration cap un-converged (in the reference too), and
 // the iterate it stops at then moves by 1e-5 relative under the blocked orthogonalisation's different rounding (measured,
 // DESIGN 9.2) -- which would shift every adjoint iteration count downstream.  It is one short solve per column.
-template <int EL, int M, int NC>
+template <int EL, int M, int NC, int RS = 1>
 __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_terminal_fast(const __grid_constant__ QgdDevProb d, const __grid_constant__ SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  const FastCtx<EL> c = make_fast_ctx<EL, M, NC, true>(d, a, smem, &extra, tmem_base);
-  const int wpc = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = c.lane;
+  const FastCtx<EL, RS> c = make_fast_ctx<EL, M, NC, true, false, RS>(d, a, smem, &extra, tmem_base);
+  const int gpc = (int)(blockDim.x >> 5) / RS, grp = (int)(threadIdx.x >> 5) / RS, lane = c.lane, vl = c.vl;  // groups per CTA (RS = 1: warps)
   const int N = d.N, N2 = d.N2;
   RegOps<EL, NC> R;
-  load_regops<EL, NC>(R, d, lane, -1);  // no preconditioner in the terminal solves
+  load_regops<EL, NC>(R, d, vl, -1);  // no preconditioner in the terminal solves
   double a_lhs[M + 1];
 #pragma unroll
   for (int j = 0; j <= M; ++j) a_lhs[j] = d.a_lhs[j];
-  const AdjOpFast<EL, M, NC> op{c, R, a_lhs};
+  const AdjOpFast<EL, M, NC, RS> op{c, R, a_lhs};
   const size_t cv_stride = (size_t)2 * (M + 1) * NC;
   const double ness2 = (double)d.Ness * (double)d.Ness, sc = 2.0 / ness2;
   const double fsc = -2.0 * d.dt / d.tf * 0.5;  // forcing[:, end, :]: trapezoid weight 1/2
   const int restart = N2 < 20 ? N2 : 20;
-  for (int b = blockIdx.x * wpc + warp; b < a.B; b += gridDim.x * wpc) {
+  for (int b = blockIdx.x * gpc + grp; b < a.B; b += gridDim.x * gpc) {
     const double* psi = a.final_all + (size_t)N2 * d.nic * b;
     double dR = 0.0, dT = 0.0;
     int tc0 = 0, tc1 = d.nic;
@@ -2156,16 +2198,16 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_terminal_fast(con
     } else {
       for (int col = 0; col < d.nic; ++col) {
         Vec<EL> p, Rt;
-        vload(p, psi + (size_t)N2 * col, N, lane);
-        vload(Rt, a.target + (size_t)N2 * col, N, lane);
+        vload(p, psi + (size_t)N2 * col, N, vl);
+        vload(Rt, a.target + (size_t)N2 * col, N, vl);
 #pragma unroll
         for (int e = 0; e < EL; ++e) {
           dR += p.u[e] * Rt.u[e] + p.v[e] * Rt.v[e];
           dT += p.u[e] * Rt.v[e] - p.v[e] * Rt.u[e];  // T = [R_v; -R_u]
         }
       }
-      dR = warp_sum(dR);
-      dT = warp_sum(dT);
+      if constexpr (RS == 1) { dR = warp_sum(dR); dT = warp_sum(dT); }
+      else { dR = row_allsum(c, dR); dT = row_allsum(c, dT); }
     }
     if (lane == 0) a.infidelity[b] = 1.0 - (dR * dR + dT * dT) / ness2;
     load_cv_fast<EL, M, NC>(c, a.cvals + ((size_t)b * (d.nsteps + 1) + d.nsteps) * cv_stride);  // controls at t = tf
@@ -2173,15 +2215,15 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_terminal_fast(con
     vzero(x);
     for (int col = tc0; col < tc1; ++col) {
       Vec<EL> p, Rt, rhs;
-      vload(p, psi + (size_t)N2 * col, N, lane);
-      vload(Rt, a.target + (size_t)N2 * col, N, lane);
+      vload(p, psi + (size_t)N2 * col, N, vl);
+      vload(Rt, a.target + (size_t)N2 * col, N, vl);
 #pragma unroll
       for (int e = 0; e < EL; ++e) {
         rhs.u[e] = (dR * Rt.u[e] + dT * Rt.v[e]) * sc + fsc * (R.wu[e] * p.u[e]);
         rhs.v[e] = (dR * Rt.v[e] + dT * (-Rt.u[e])) * sc + fsc * (R.wv[e] * p.v[e]);
       }
       const int it = gmres_fast_strict<EL, NC>(c, R, op, x, rhs, d.abstol, restart, N2, d.reltol);
-      vstore(x, a.terminal_out + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, lane);
+      vstore(x, a.terminal_out + (size_t)N2 * ((size_t)col + (size_t)d.nic * b), N, vl);
       if (a.iters_term && lane == 0) a.iters_term[(size_t)col + (size_t)d.nic * b] = it;
     }
   }

@@ -172,6 +172,14 @@ void launch_backward_fast_rs_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   ensure_krylov_fast(h, L, 2, d.N2, a);
   launch_sweep(h, kernel, L, d, a, (const QgdDevControl*)h->d_ctrls.as<QgdDevControl>());
 }
+template <int M, int NC, int RS>
+void launch_terminal_fast_rs_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
+  const int restart = std::min(20, d.N2);
+  auto kernel = k_terminal_fast<2, M, NC, RS>;
+  FastCfg L = plan_fast(h, kernel, fast_fixed_doubles<2, M, NC, true, RS>(d.N2), 2, (size_t)a.B, 0, restart, RS, group_doubles<2, RS>());
+  ensure_krylov_fast(h, L, 2, restart, a);
+  launch_sweep(h, kernel, L, d, a);
+}
 template <int EL, int M, int NC>
 void launch_terminal_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   const int restart = std::min(20, d.N2);
@@ -255,7 +263,11 @@ void launch_backward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   }                                                                                                                         \
   bool launch_backward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                          \
     QGD_FAST_CASE_RS(backward, M, 2, 2) QGD_FAST_CASE_RS(backward, M, 3, 2) QGD_FAST_CASE_RS(backward, M, 2, 4)               \
-    QGD_FAST_CASE_RS(backward, M, 3, 4) QGD_FAST_CASE_RS(backward, M, 4, 2) QGD_FAST_CASE_RS(backward, M, 4, 4) return false;                                                                       \
+    QGD_FAST_CASE_RS(backward, M, 3, 4) QGD_FAST_CASE_RS(backward, M, 4, 2) QGD_FAST_CASE_RS(backward, M, 4, 4) return false; \
+  }                                                                                                                         \
+  bool launch_terminal_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                          \
+    QGD_FAST_CASE_RS(terminal, M, 2, 2) QGD_FAST_CASE_RS(terminal, M, 3, 2) QGD_FAST_CASE_RS(terminal, M, 2, 4)               \
+    QGD_FAST_CASE_RS(terminal, M, 3, 4) QGD_FAST_CASE_RS(terminal, M, 4, 2) QGD_FAST_CASE_RS(terminal, M, 4, 4) return false; \
   }
 
 // The latency team (four warps per column) in translation units of its own.

@@ -630,9 +630,12 @@ def test_row_split_sweeps_vs_oracle_and_generic_kernels(q, O, sizes, order, nste
     # (6,6,6): the reference's un-preconditioned GMRES(20) terminal solve stops at its 2N-iteration cap un-converged there, and
     # what it stops at is rounding-sensitive: oracle, generic kernels and these sweeps (which all take lambda_N
     # from that solve) then differ by 1e-6 in the gradient while every forward quantity agrees to 1e-10
+    # (tools/gpu/term_check_rs.py: at these sizes EVERY terminal solve stops at the cap; lambda_N of the strict generic kernel and
+    # of these sweeps' terminal kernel then differ from the oracle's by 4e-15 ... 9e-7 depending on the case, alike)
     capped = int(out["iters_term"].max()) >= 2 * prob.N_tot_levels
-    assert capped or sizes != (6, 6, 6)
-    gtol = 1e-5 if sizes == (6, 6, 6) else RTOL
+    loose = {((6, 6, 6), 8): 1e-5, ((5, 5, 5), 12): 1e-8}.get((sizes, order))
+    assert capped or loose is None
+    gtol = loose or RTOL
     assert rel(out["history"][..., 0], ref["history"]) < RTOL
     assert rel(out["grad"][:, 0], ref["grad"]) < gtol
     assert rel(out["grad"], gen["grad"]) < gtol
