@@ -1,9 +1,10 @@
 // qgd_fast.cuh -- register-resident-operator sweep kernels (sm_100a): the hot path for the problems the
 // reference is built around (DispersiveProblem-style: diagonal drift, control operators with at most two
 // entries per row such as a +- a^dagger, diagonal guard projector, Identity or DiagonalHamiltonian
-// preconditioner, N_tot_levels <= 64).  Everything else runs on the generic kernels of qgd_kernels.cuh.
+// preconditioner, N_tot_levels <= 256).  Everything else runs on the generic kernels of qgd_kernels.cuh.
 //
-// One warp = one initial-condition column of one control vector, marching all time steps on-device.
+// One warp = one initial-condition column of one control vector, marching all time steps on-device (N <= 64; for
+// 64 < N <= 256 a row-split group of two or four warps, FastCtx RS below).
 //   * Hamiltonian blocks live in REGISTERS (values + gather columns of the <= 2 entries per row and
 //     operator), the state is exchanged between lanes through a 16-byte (u,v)-interleaved shared-memory
 //     buffer (one LDS.128 per gathered entry).
