@@ -243,9 +243,11 @@ def test_many_short_lived_problems_through_the_api(q, O):
 
 
 # ---- multi-GPU inside the library --------------------------------------------------------------------------------
-def test_communicator_of_one_rank_matches_plain_handle(q):
-    """The collective code path (NCCL all-reduces enqueued on the sweep stream) on one GPU: a communicator of ONE rank."""
-    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
+@pytest.mark.parametrize("sizes", [(3, 3, 3), (5, 4, 4)])
+def test_communicator_of_one_rank_matches_plain_handle(q, sizes):
+    """The collective code path (NCCL all-reduces enqueued on the sweep stream) on one GPU: a communicator of ONE rank.
+    (5,4,4): a row-split problem (two warps per column; its terminal kernel in the scalar-exchange mode too)."""
+    prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14 if sizes == (3, 3, 3) else 1e-12, subsystem_sizes=sizes, D1=5)
     tgt = q.complex_to_real(target)
     pcs = np.stack([pcof, 0.5 * pcof], axis=1)
     plain = q.Handle(prob, controls)
@@ -257,7 +259,8 @@ def test_communicator_of_one_rank_matches_plain_handle(q):
         h.set_option(q.backend.OPT_TERMINAL_EXCHANGE, exchange)
         out = h.discrete_adjoint(pcs, tgt, order=order)
         assert h.stats()["collectives"] == 2
-        assert rel(out["grad"], ref["grad"]) < 1e-12
+        # (5,4,4): the terminal solve stops at its iteration cap and amplifies the last-bit difference of the exchanged overlaps
+        assert rel(out["grad"], ref["grad"]) < (1e-12 if sizes == (3, 3, 3) else 1e-8)
         assert np.allclose(out["infidelity"], ref["infidelity"], rtol=1e-13, atol=0)
         assert np.allclose(out["guard_penalty"], ref["guard_penalty"], rtol=1e-13, atol=1e-300)
         h.comm_finalize()
