@@ -742,3 +742,17 @@ def test_row_split_sweeps_identity_preconditioner_lambda_history_and_save_every(
     some = h.eval_forward(pcof, order=order, save_every=3)
     assert np.array_equal(some["history"][:, :, :, :, 0], out["history"][:, :, ::3, :, 0])
     h.close()
+
+
+def test_forced_gradient_on_a_row_split_problem_runs_on_the_generic_kernels(q, O):
+    """eval_grad_forced at N = 80: the forward sweep that leaves the history takes the row-split groups, the P x nic forced
+    solves the generic kernels (forced sweeps exist for one-warp columns only); equal to the oracle's forced gradient."""
+    prob, controls, U0 = _dispersive(q, (5, 4, 4), 4)
+    P = q.get_number_of_control_parameters(controls)
+    pcof = q.configs.cnot3_pcof(P, 5)
+    gf = q.eval_grad_forced(prob, controls, pcof, U0, order=4)
+    st = q.get_handle(prob, controls).stats()
+    assert st["fast_path_launches"] == 1, st   # the unforced forward sweep only
+    ref = O.eval_grad_forced(prob, controls, pcof, U0, order=4)
+    assert rel(gf, ref) < RTOL
+    q.backend.clear_handles()

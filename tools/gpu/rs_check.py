@@ -50,9 +50,8 @@ if "--time" not in sys.argv:
         print("   rs vs generic grad", f"{rel(res['rs']['grad'], res['generic']['grad']):.2e}")
         h.close()
 else:
-    for sizes in ((5, 5, 5), (6, 6, 6)):
+    for sizes, B in (((5, 5, 5), 74), ((6, 6, 6), 74), ((5, 5, 5), 1), ((6, 6, 6), 1)):
         prob, controls, P, U0 = problem(sizes, 60, D1=10)
-        B = 74
         pcs = np.asfortranarray(np.stack([q.configs.cnot3_pcof(P, s) for s in range(B)], axis=1))
         h = q.Handle(prob, controls)
         r = {}
@@ -61,7 +60,8 @@ else:
             for rep in range(2):
                 out = h.discrete_adjoint(pcs, q.complex_to_real(U0), order=8, want_iters=(rep == 1))
             st = h.stats()
-            r[name] = dict(fwd_ms=round(st["last_forward_ms"], 1), bwd_ms=round(st["last_backward_ms"], 1), fast=st["fast_path_launches"], its=float(out["iters_fwd"].mean()))
+            r[name] = dict(fwd_ms=round(st["last_forward_ms"], 1), bwd_ms=round(st["last_backward_ms"], 1), total_ms=round(st["last_total_ms"], 1),
+                           fast=st["fast_path_launches"], its=float(out["iters_fwd"].mean()))
             r[name + "_grad"] = out["grad"]
         print(json.dumps(dict(sizes=sizes, batch=B, nsteps=60, rs=r["rs"], generic=r["generic"], grad_rel=rel(r["rs_grad"], r["generic_grad"]))), flush=True)
         h.close()
