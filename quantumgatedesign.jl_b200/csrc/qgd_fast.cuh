@@ -471,7 +471,6 @@ __device__ __forceinline__ void adj_fast(const FastCtx<EL, RS>& c, const RegOps<
   for (int j = 0; j <= M; ++j) { what[j] = x; vscale(what[j], alpha[j]); }
   Vec<EL> wh[M];
   if (GRAD) {
-#pragma unroll
     if (last_use) {
 #pragma unroll
       for (int i = 0; i < M; ++i) vload_cs(wh[i], hist + (size_t)i * N2, N, lane);

@@ -65,6 +65,7 @@ __device__ __forceinline__ double warp_sum_dmma(double p) {
   double c0, c1, t0, t1;
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(c0), "=d"(c1) : "d"(1.0), "d"(p), "d"(0.0), "d"(0.0));
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(t0), "=d"(t1) : "d"(c0 + c1), "d"(1.0), "d"(0.0), "d"(0.0));
+  (void)t1;
   return t0;
 }
 #ifndef QGD_GENERIC_DMMA_RED

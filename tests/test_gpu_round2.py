@@ -756,3 +756,23 @@ def test_forced_gradient_on_a_row_split_problem_runs_on_the_generic_kernels(q, O
     ref = O.eval_grad_forced(prob, controls, pcof, U0, order=4)
     assert rel(gf, ref) < RTOL
     q.backend.clear_handles()
+
+
+def test_row_split_sweeps_sixty_steps_iteration_counts(q, O):
+    """(5,5,5) levels, 60 steps, order 8 (the shape of the mid-size bench extra): every one of the 960 GMRES solves of a gradient
+    evaluation takes the oracle's number of iterations (about 150 per step); history and infidelity to 1e-10."""
+    prob, controls, U0 = _dispersive(q, (5, 5, 5), 60, D1=10)
+    P = q.get_number_of_control_parameters(controls)
+    pcof = q.configs.cnot3_pcof(P, 0)
+    ref = O.discrete_adjoint(prob, controls, pcof, U0, order=8)
+    h = q.Handle(prob, controls)
+    out = h.discrete_adjoint(pcof, q.complex_to_real(U0), order=8, want_iters=True, want_history=True)
+    assert h.stats()["fast_path_launches"] == 2
+    h.close()
+    mf = int((out["iters_fwd"][:, :, 0] != ref["iters_fwd"]).sum()); ma = int((out["iters_adj"][:, :, 0] != ref["iters_adj"]).sum())
+    print("N = 125, 60 steps: iterations", int(ref["iters_fwd"].sum() + ref["iters_adj"].sum()), "mismatching solves", mf, ma,
+          "grad rel", rel(out["grad"][:, 0], ref["grad"]))
+    assert rel(out["history"][..., 0], ref["history"]) < RTOL
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * max(abs(ref["infidelity"]), 1e-12)
+    assert mf + ma <= 2 and np.abs(out["iters_fwd"][:, :, 0] - ref["iters_fwd"]).max() <= 1 and np.abs(out["iters_adj"][:, :, 0] - ref["iters_adj"]).max() <= 1
+    assert rel(out["grad"][:, 0], ref["grad"]) < 1e-8   # lambda_N from the capped terminal solve (profiles/r02_row_split_groups.txt)
