@@ -301,10 +301,12 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs on the box")
-@pytest.mark.parametrize("case", ["cnot3_333", "dense32"])
+@pytest.mark.parametrize("case", ["cnot3_333", "dense32", "cnot3_544_row_split"])
 def test_multi_gpu_column_sharding_matches_single_handle(q, case):
     if case == "cnot3_333":
         prob, controls, pcof, target, order = q.configs.cnot3(nsteps=8, tf=8.0, gmres_tol=1e-14, subsystem_sizes=(3, 3, 3), D1=5)
+    elif case == "cnot3_544_row_split":  # two warps per column; the columns of a control vector on different GPUs
+        prob, controls, pcof, target, order = q.configs.cnot3(nsteps=6, tf=6.0, gmres_tol=1e-12, subsystem_sizes=(5, 4, 4), D1=5)
     else:
         prob, controls, pcof, target, order = q.configs.dense_random(N=32, nic=11, Nc=2, nsteps=5, order=8, gmres_tol=1e-13, dt_norm=0.5)
     tgt = q.complex_to_real(target)
@@ -315,7 +317,7 @@ def test_multi_gpu_column_sharding_matches_single_handle(q, case):
     n = min(_ngpu(), 4)
     mg = q.backend.MultiGPU(prob, controls, n)
     cols = mg.discrete_adjoint(pcs, tgt, order=order, shard=q.backend.SHARD_COLUMNS)
-    assert rel(cols["grad"], ref["grad"]) < 1e-12
+    assert rel(cols["grad"], ref["grad"]) < (1e-10 if case == "cnot3_544_row_split" else 1e-12)
     assert np.allclose(cols["infidelity"], ref["infidelity"], rtol=1e-13, atol=0)
     assert np.allclose(cols["guard_penalty"], ref["guard_penalty"], rtol=1e-12, atol=1e-300)
     vecs = mg.discrete_adjoint(pcs, tgt, order=order, shard=q.backend.SHARD_CONTROL_VECTORS)
