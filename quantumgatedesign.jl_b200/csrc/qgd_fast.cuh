@@ -176,6 +176,7 @@ struct FastCtx {
   double2* gx;    // RS > 1: smem [2][32 EL RS] gather buffer of the group
   double* gred;   // RS > 1: smem [2][RS][8] partial sums of the group (double buffered: one barrier per reduction)
   unsigned* gtick;  // RS > 1: smem ticket word of the group
+  double2* stage;   // RS > 1: smem [8][32 EL] staging block of the L2 tier (the last 8 slots of the shared-memory tier), or null
   mutable unsigned par;  // RS > 1: parity of the next reduction
   int KT, KS;     // Krylov vectors [0,KT) live in TMEM, [KT,KT+KS) in shared memory, the rest in L2
   uint32_t tm;    // TMEM address of this warp's region (its 32 lanes, its column range)
@@ -1000,10 +1001,60 @@ __device__ __forceinline__ void gs_block(const FastCtx<EL, RS>& c, int i0, int n
     if (q < nb) vaxpy(w, -h[q], vb[q]);
 }
 
+// Row-split groups run Krylov spaces of 150-250 vectors of which 40-48 per warp are on chip: the L2 tier is most of the basis
+// and a warp has no registers left to prefetch it.  The block after the current one is therefore copied L2 -> shared memory
+// by cp.async (LDGSTS) into a staging block carved from the shared-memory tier (QGD_RS_STAGE_L2), the first L2 block of an
+// orthogonalisation already while the TMEM and shared-memory tiers are being swept.  Every lane copies and later reads only
+// its own 16-byte slots, so cp.async.wait_group is the only synchronisation.
+// MEASURED ON B200 (round 2, profiles/r02_row_split_groups.txt): correct (all parity tests green) but SLOWER -- N = 125, 74 control
+// vectors x 60 steps: forward 109 -> 125 ms, adjoint 166 -> 171 ms; one evaluation 158 -> 165 ms.  The staging block costs 8 of the
+// 16 resident shared-memory vectors, the staged path needs the one-copy loop shape that costs the forward kernel its three
+// specialised tier loops, and the extra shared-memory round trip of every L2 block is not cheaper than the exposed L2 latency it
+// replaces.  Off by default; kept as the record of the experiment.
+#ifndef QGD_RS_STAGE_L2
+#define QGD_RS_STAGE_L2 0
+#endif
+__device__ __forceinline__ void cp16(double2* dst_smem, const double2* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+template <int EL, int RS>
+__device__ __forceinline__ void stage_issue(const FastCtx<EL, RS>& c, int i0) {  // L2-tier block i0 .. i0+7 -> staging
+  const double2* p = c.Vg + (size_t)(i0 - c.KT - c.KS) * 32 * EL + c.lane;
+  double2* dst = c.stage + c.lane;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int e = 0; e < EL; ++e) cp16(dst + q * 32 * EL + 32 * e, p + q * 32 * EL + 32 * e);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int EL, int RS>
+__device__ __forceinline__ void stage_take(const FastCtx<EL, RS>& c, Vec<EL> (&vb)[8]) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v2_load<EL>(vb[q], c.stage + (size_t)q * 32 * EL, c.lane);
+}
+
 // w is orthogonalised against V[:, 0..k-1]; c.hcol[0..k-1] receives the coefficients.
 template <int EL, int BLK, int VARIANT, int RS>
 __device__ __forceinline__ void gs_orthogonalize(const FastCtx<EL, RS>& c, int k, Vec<EL>& w) {
   __syncwarp();  // the gather buffer (read by the operator application) becomes the transposition buffer
+  if constexpr (RS > 1 && QGD_RS_STAGE_L2 && BLK == 8) {
+    if (c.stage != nullptr) {
+      const int bT = c.KT, bS = c.KT + c.KS;
+      if (k > bS) stage_issue(c, bS);
+      for (int i0 = 0; i0 < k; i0 += 8) {
+        Vec<EL> vb[8];
+        if (i0 < bT) gs_load_block<EL, 8, 0>(c, i0, vb);
+        else if (i0 < bS) gs_load_block<EL, 8, 1>(c, i0, vb);
+        else {
+          stage_take(c, vb);
+          if (i0 + 8 < k) stage_issue(c, i0 + 8);
+        }
+        gs_block<EL, 8, VARIANT>(c, i0, k - i0, vb, w);
+      }
+      return;
+    }
+  }
   if constexpr ((VARIANT & 1) != 0) {
   // one copy of the block arithmetic for the three tiers: the hot loop has to fit the 32 KB instruction cache
   const int bT = c.KT, bS = c.KT + c.KS;
@@ -1765,7 +1816,7 @@ __device__ __forceinline__ FastCtx<EL, RS> make_fast_ctx(const QgdDevProb& d, co
   c.bar = 1 + (int)((threadIdx.x >> 5) / RS);
   c.vl = c.lane + 32 * EL * c.slice;
   c.par = 0u;
-  c.gx = nullptr; c.gred = nullptr; c.gtick = nullptr;
+  c.gx = nullptr; c.gred = nullptr; c.gtick = nullptr; c.stage = nullptr;
   if constexpr (RS > 1) {  // group regions behind the warp regions
     double* gbase = reinterpret_cast<double*>(smem + 16) + (size_t)(blockDim.x >> 5) * a.warp_smem_doubles +
                     (size_t)((threadIdx.x >> 5) / RS) * group_doubles<EL, RS>();
@@ -1802,6 +1853,9 @@ __device__ __forceinline__ FastCtx<EL, RS> make_fast_ctx(const QgdDevProb& d, co
   c.g = w; w += d.N2 + 2;
 #endif
   c.Vs = reinterpret_cast<double2*>(w); w += (size_t)a.ks * 2 * 32 * EL;
+  if constexpr (RS > 1) {
+    if (a.stage_l2) { c.stage = reinterpret_cast<double2*>(w); w += (size_t)8 * 2 * 32 * EL; }
+  }
   double* hs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w) + 31) & ~(uintptr_t)31);  // 32-byte aligned columns (hpk)
   w += a.h_smem_doubles;
   c.team = nullptr;

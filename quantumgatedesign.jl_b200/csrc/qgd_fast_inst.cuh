@@ -10,7 +10,7 @@
 namespace {
 using namespace qgd;
 
-struct FastCfg { int grid, threads, wpc, ks, kt, tmem_cols, warp_doubles, h_smem; size_t smem; };
+struct FastCfg { int grid, threads, wpc, ks, kt, tmem_cols, warp_doubles, h_smem, stage_l2; size_t smem; };
 
 // One CTA per SM, all of its shared memory split between the warps; whatever is left after the fixed
 // per-warp arrays holds the resident part of the Krylov basis.
@@ -54,6 +54,10 @@ FastCfg plan_fast(qgd_handle* h, K kernel, int fixed_doubles, int el, size_t ite
   if (ks < 0) throw QgdError(QGD_EUNSUPPORTED, "fast path: shared memory too small for the per-warp state");
   L.ks = (int)(ks / blk) * blk;
   ks = L.ks;
+  // row-split groups: when part of the basis has to live in L2, the last block of the shared-memory tier becomes the staging
+  // block its L2 tier is prefetched into (qgd_fast.cuh, QGD_RS_STAGE_L2)
+  L.stage_l2 = 0;
+  if (rs > 1 && QGD_RS_STAGE_L2 && blk == 8 && L.ks >= 16 && restart + 1 > L.kt + L.ks) { L.stage_l2 = 1; L.ks -= 8; }
   L.warp_doubles = base + (int)ks * vec + L.h_smem;
   L.threads = 32 * L.wpc;
   L.smem = 16 + ((size_t)L.wpc * L.warp_doubles + (size_t)ngroups * group_dbl) * 8;
@@ -107,7 +111,7 @@ void ensure_krylov_fast(qgd_handle* h, const FastCfg& L, int el, int restart, Sw
   a.progress = h->d_progress.as<int>();
   h->d_carry.reserve(std::max<size_t>(items, 1) * (size_t)h->N2 * 8);
   a.carry = h->d_carry.as<double>();
-  a.ks = L.ks; a.kt = L.kt; a.tmem_cols = L.tmem_cols; a.h_smem_doubles = L.h_smem;
+  a.ks = L.ks; a.kt = L.kt; a.tmem_cols = L.tmem_cols; a.h_smem_doubles = L.h_smem; a.stage_l2 = L.stage_l2;
   a.warp_smem_doubles = L.warp_doubles;
 }
 

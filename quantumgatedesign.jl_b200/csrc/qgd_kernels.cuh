@@ -25,6 +25,7 @@ struct SweepArgs {
   int kt;                // fast path: Krylov basis vectors resident in tensor memory per warp
   int tmem_cols;         // fast path: TMEM columns the CTA allocates (0: none; power of two >= 32)
   int h_smem_doubles;    // fast path: > 0: the packed Hessenberg matrix of a warp lives in shared memory (few columns in flight)
+  int stage_l2;          // fast path, row-split groups: 1 = a staging block for the L2 tier follows the shared-memory tier
   unsigned int* work_counter;  // fast path: ticket queue head (zeroed before the launch)
   int seg_steps;         // fast path: time steps per ticket
   int* progress;         // fast path: [items] segments published per item (zeroed before the launch)
