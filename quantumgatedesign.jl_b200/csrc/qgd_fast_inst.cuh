@@ -200,8 +200,9 @@ void launch_derivs_fast_t(qgd_handle* h, QgdDevProb d, SweepArgs a, double* uv, 
   h->stats.kernel_launches++;
 }
 
-// (EL, NC) shapes built for every M: N <= 32 with 1..4 control operators (four two-level qubits: N = 16), N <= 64 with 2..3.
-#define QGD_FAST_SHAPES(X, M) X(1, M, 1) X(1, M, 2) X(1, M, 3) X(1, M, 4) X(2, M, 2) X(2, M, 3)
+// (EL, NC) shapes built for every M: N <= 32 with 1..4 control operators (four two-level qubits: N = 16), N <= 64 with 2..4
+// (four qubits with guard levels on some: (3,3,2,2) = 36 ... (3,3,3,2) = 54 levels).
+#define QGD_FAST_SHAPES(X, M) X(1, M, 1) X(1, M, 2) X(1, M, 3) X(1, M, 4) X(2, M, 2) X(2, M, 3) X(2, M, 4)
 
 }  // namespace
 

@@ -688,10 +688,10 @@ def _four_qubits(q, sizes, nsteps, tol=1e-12):
     return prob, controls, q.create_initial_conditions(sizes, ess)
 
 
-@pytest.mark.parametrize("sizes,order,nsteps", [((2, 2, 2, 2), 8, 8), ((3, 3, 3, 3), 6, 4), ((4, 4, 4, 4), 4, 2)])
+@pytest.mark.parametrize("sizes,order,nsteps", [((2, 2, 2, 2), 8, 8), ((3, 3, 2, 2), 8, 6), ((3, 3, 3, 3), 6, 4), ((4, 4, 4, 4), 4, 2)])
 def test_four_control_operators_on_the_register_operator_sweeps(q, O, sizes, order, nsteps):
-    """Four qubits: N = 16 on one warp per column, N = 81 on two, N = 256 on four -- Nc = 4 shapes of the register-operator
-    sweeps; against the oracle and the generic kernels."""
+    """Four qubits: N = 16 and N = 36 on one warp per column (one and two level rows per lane), N = 81 on two warps, N = 256 on
+    four -- Nc = 4 shapes of the register-operator sweeps; against the oracle and the generic kernels."""
     prob, controls, U0 = _four_qubits(q, sizes, nsteps)
     P = q.get_number_of_control_parameters(controls)
     pcof = 0.02 * (np.random.default_rng(3).random(P) - 0.5)
