@@ -778,3 +778,71 @@ def test_row_split_sweeps_sixty_steps_iteration_counts(q, O):
     assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * max(abs(ref["infidelity"]), 1e-12)
     assert mf + ma <= 2 and np.abs(out["iters_fwd"][:, :, 0] - ref["iters_fwd"]).max() <= 1 and np.abs(out["iters_adj"][:, :, 0] - ref["iters_adj"]).max() <= 1
     assert rel(out["grad"][:, 0], ref["grad"]) < 1e-8   # lambda_N from the capped terminal solve (profiles/r02_row_split_groups.txt)
+
+
+def _random_row_split_case(q, seed):
+    """Seeded dispersive problems with 64 < N <= 256 (two to four subsystems), random essential levels, couplings, control families,
+    Identity / Diagonal preconditioner, orders 2-12, random complex target."""
+    rng = np.random.default_rng(7000 + seed)
+    while True:
+        nsub = int(rng.integers(2, 5))
+        sizes = tuple(int(rng.integers(2, 8 if nsub == 2 else 7)) for _ in range(nsub))
+        n = int(np.prod(sizes))
+        if 64 < n <= 256 and (nsub < 4 or True):
+            break
+    ess = tuple(int(rng.integers(1, min(s, 3) + 1)) for s in sizes)
+    order = int(rng.choice([2, 4, 6, 8, 10, 12]))
+    nsteps = int(rng.integers(2, 6))
+    tf = float(nsteps) * float(rng.choice([0.5, 1.0]))
+    freqs = 2 * np.pi * rng.uniform(3.5, 8.0, nsub)
+    kerr = 2 * np.pi * 0.2 * rng.random((nsub, nsub))
+    kerr = 0.5 * (kerr + kerr.T)
+    pre = [q.IdentityPreconditioner, q.DiagonalHamiltonianPreconditioner][int(rng.integers(0, 2))]
+    prob = q.DispersiveProblem(sizes, ess, freqs, freqs, kerr, tf, nsteps, sparse_rep=True, gmres_abstol=1e-12, gmres_reltol=1e-12,
+                               preconditioner_type=pre)
+    controls = []
+    for k in range(prob.N_operators):
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            c = q.GRAPEControl(int(rng.integers(1, 6)), prob.tf)
+        elif kind == 1:
+            c = q.BSpline2Control(int(rng.integers(3, 9)), prob.tf)
+        elif kind == 2:
+            deg = int(rng.choice([2, 4, 8, 14]))
+            c = q.FortranBSplineControl(deg, deg + int(rng.integers(2, 8)), prob.tf)
+        else:
+            c = q.CarrierControl(q.BSpline2Control(int(rng.integers(3, 7)), prob.tf), list(rng.uniform(-3, 3, int(rng.integers(1, 4)))))
+        controls.append(c)
+    P = q.get_number_of_control_parameters(controls)
+    pcof = 0.05 * rng.standard_normal(P)
+    nic = prob.N_initial_conditions
+    target = (rng.standard_normal((n, nic)) + 1j * rng.standard_normal((n, nic))) / np.sqrt(n)
+    return prob, controls, pcof, target, order, f"dispersive {sizes}/{ess} N={n} nic={nic} Nc={nsub} precond {pre.__name__ if hasattr(pre, '__name__') else pre} order {order} nsteps {nsteps}"
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_seeded_random_row_split_problems_vs_oracle(q, O, seed):
+    """Random problems of the row-split sizes on the DEFAULT path (the seeded cases above run strict orthogonalisation, which these
+    sizes take on the generic kernels): state history to 1e-10, GMRES iteration counts within one, gradient against the oracle and
+    the generic kernels at the rounding sensitivity of the capped terminal solve."""
+    prob, controls, pcof, target, order, desc = _random_row_split_case(q, seed)
+    tgt = q.complex_to_real(target)
+    h = q.Handle(prob, controls)
+    f0 = h.stats()["fast_path_launches"]
+    out = h.discrete_adjoint(pcof, tgt, order=order, want_history=True, want_iters=True)
+    fast = h.stats()["fast_path_launches"] - f0
+    h.set_option(q.backend.OPT_DISABLE_FAST, 1)
+    gen = h.discrete_adjoint(pcof, tgt, order=order)
+    h.close()
+    ref = O.discrete_adjoint(prob, controls, pcof, target, order=order)
+    print(desc, "| register-operator sweeps:", fast, "| it/step", float(ref["iters_fwd"].mean()), "| grad rel", rel(out["grad"][:, 0], ref["grad"]),
+          "| iters_term max", int(out["iters_term"].max()))
+    assert fast == (2 if prob.N_operators in (2, 3, 4) else 0), desc
+    assert rel(out["history"][..., 0], ref["history"]) < RTOL, desc
+    assert abs(out["infidelity"][0] - ref["infidelity"]) <= RTOL * max(abs(ref["infidelity"]), 1e-12), desc
+    assert abs(out["guard_penalty"][0] - ref["guard_penalty"]) <= RTOL * max(abs(ref["guard_penalty"]), 1e-12), desc
+    assert np.abs(out["iters_fwd"][:, :, 0] - ref["iters_fwd"]).max() <= 1 and np.abs(out["iters_adj"][:, :, 0] - ref["iters_adj"]).max() <= 1, desc
+    capped = int(out["iters_term"].max()) >= 2 * prob.N_tot_levels
+    gtol = 1e-6 if capped else RTOL
+    assert rel(out["grad"][:, 0], ref["grad"]) < gtol, desc
+    assert rel(out["grad"], gen["grad"]) < gtol, desc
