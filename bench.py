@@ -609,7 +609,12 @@ def c4_measure(q, torch, dist, rank, world, local, nsteps, B, steps, warmup, wit
     clocks = sampler.stop() if rank == 0 else None
     itf, ita = out["iters_fwd"], out["iters_adj"]
     evals = (2 * nsteps + 1) * 256 * B + itf.sum() + (3 * nsteps - 1) * 256 * B + ita.sum()
-    flops = 8.0 * 256 ** 2 * (m * (m + 1) / 2) * float(evals)  # K_d, S_d pre-combined: 8 N^2 per application and column
+    flops_ops = 8.0 * 256 ** 2 * (m * (m + 1) / 2) * float(evals)  # K_d, S_d pre-combined: 8 N^2 per application and column
+    # F_alg also holds the gradient inner products F_ip.  Counted in their minimal form -- per time step and column
+    # the m Nc products K_k w, S_k w of ONE fused gradient sweep (8 N^2 each), not the reference's 2 Nc m(m+1) mat-vecs per side
+    nctrl = 4
+    flops_ip = 8.0 * 256 ** 2 * m * nctrl * float(nsteps) * 256 * B
+    flops = flops_ops + flops_ip
     t = torch.tensor([wall, dev_ms * 1e-3], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -637,7 +642,8 @@ def c4_measure(q, torch, dist, rank, world, local, nsteps, B, steps, warmup, wit
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "k_forward_dense + k_backward_dense (FP64 DMMA)", "achieved": ach, "peak": dmma_peak,
                      "unit": "TFLOP/s", "frac": ach / dmma_peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_flops_per_step": flops},
+                     "algorithmic_flops_per_step": flops,
+                     "algorithmic_flops_breakdown": {"operator_applications": flops_ops, "gradient_contractions_minimal_form": flops_ip}},
         "kernel_ms": {"k_forward_dense": st["last_forward_ms"], "k_backward_dense": st["last_backward_ms"], "device_total": st["last_total_ms"]},
         "gmres_iterations_per_step_and_column": {"forward": float(itf.mean()), "backward": float(ita.mean())},
         "cpu_baseline": c4_cpu_sample(q, nsteps) if (with_cpu and world == 1) else None,
