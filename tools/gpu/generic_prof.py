@@ -1,4 +1,5 @@
-"""One short forward sweep of the sparse N = 125 problem on the generic kernels (for ncu)."""
+"""One short forward sweep of the sparse N = 125 problem (for ncu).  Since the row-split groups exist it runs on the register-operator
+sweeps (two warps per column: profiles/r02_ncu_rs_fwd.txt); `--generic` forces the row-ELL kernels it was first written for."""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -11,5 +12,7 @@ controls = [q.CarrierControl(q.BSpline2Control(10, 60.0), [0.0, -kerr[k, (k + 1)
 P = q.get_number_of_control_parameters(controls)
 pcs = np.asfortranarray(np.stack([q.configs.cnot3_pcof(P, s) for s in range(74)], axis=1))
 h = q.Handle(prob, controls)
+if "--generic" in sys.argv:
+    h.set_option(q.backend.OPT_DISABLE_FAST, 1)
 out = h.eval_forward(pcs, order=8, want_history=False, want_iters=True)
 print("iters/step", out["iters"].mean(), "fwd ms", h.stats()["last_forward_ms"])

@@ -1,5 +1,7 @@
 """Time the GENERIC row-ELL sweeps (everything that is neither a register-operator nor a dense tensor-core problem):
-C2 forced onto them (QGD_OPT_DISABLE_FAST) and a sparse (5,5,5)-level dispersive problem (N = 125, which has no fast path).
+C2 forced onto them (QGD_OPT_DISABLE_FAST) and a sparse (5,5,5)-level dispersive problem (N = 125; it had no fast path when this was
+written -- the row-split groups serve it now, so the problem is forced onto the generic kernels as well; tools/gpu/rs_check.py
+compares the two).
 usage: python tools/gpu/generic_time.py"""
 import json
 import sys
@@ -39,6 +41,7 @@ P = q.get_number_of_control_parameters(controls)
 pcs = np.asfortranarray(np.stack([q.configs.cnot3_pcof(P, s) for s in range(74)], axis=1))
 U0 = q.create_initial_conditions((5, 5, 5), (2, 2, 2))
 h = q.Handle(prob, controls)
+h.set_option(q.backend.OPT_DISABLE_FAST, 1)
 for rep in range(2):
     out = h.discrete_adjoint(pcs, q.complex_to_real(U0), order=8, want_iters=(rep == 1))
 st = h.stats()
