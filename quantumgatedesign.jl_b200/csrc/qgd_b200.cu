@@ -565,7 +565,8 @@ bool try_backward_fast_rs(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a
   QGD_FAST_SWITCH(d.m, launch_backward_fast_rs, h, d, a, h->fast_rs, h->Nc)
 }
 bool try_forward_fast_forced(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {  // forced solves: eval_forward!(...; forcing), eval_grad_forced
-  if (!fast_applicable(h, d.m) || h->fast_rs > 1) return false;
+  if (!fast_applicable(h, d.m)) return false;
+  if (h->fast_rs > 1) { QGD_FAST_SWITCH(d.m, launch_forward_fast_forced_rs, h, d, a, h->fast_rs, h->Nc) }
   QGD_FAST_SWITCH(d.m, launch_forward_fast_forced, h, d, a, h->fast_el, h->Nc)
 }
 bool try_forward_fast_team(qgd_handle* h, const QgdDevProb& d, const SweepArgs& a) {

@@ -1877,7 +1877,6 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
   extern __shared__ __align__(16) unsigned char smem[];
   double* extra;
   const uint32_t tmem_base = a.tmem_cols ? tmem_alloc_cols(reinterpret_cast<uint32_t*>(smem), (uint32_t)a.tmem_cols) : 0u;
-  static_assert(RS == 1 || !FORCED, "forced solves of row-split problems run on the generic kernels");
   const FastCtx<EL, RS> c = make_fast_ctx<EL, M, NC, STRICT, TEAM, RS>(d, a, smem, &extra, tmem_base);
   if constexpr (TEAM) {
     if ((threadIdx.x >> 5) > 0) {
@@ -1928,7 +1927,7 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
     double gpen = 0.0;
     auto guard_cross = [&](const Vec<EL>& dx, int n) {
       Vec<EL> w0;
-      vload_cg(w0, hb + slot_sz * n, N, lane);
+      vload_cg(w0, hb + slot_sz * n, N, vl);
       const double wt = (n == 0 || n == d.nsteps) ? 1.0 : 2.0;
 #pragma unroll
       for (int e = 0; e < EL; ++e) gpen = fma(wt * R.wu[e] * dx.u[e], w0.u[e], fma(wt * R.wv[e] * dx.v[e], w0.v[e], gpen));
@@ -1977,9 +1976,9 @@ __global__ void __launch_bounds__(32 * QGD_WARPS_PER_CTA, 1) k_forward_fast(cons
     vstore(x, carry, N, vl);
     if constexpr (FORCED) {
       if (gradf) {  // guard-penalty derivative partial of this segment; the sum is carried in guardcol across segments
-        const double g = warp_allsum(gpen) * (d.dt / d.tf);
+        const double g = row_allsum(c, gpen) * (d.dt / d.tf);
         double* gc = a.guardcol + ((size_t)cl + (size_t)d.ncol * b);
-        if (lane == 0) *gc = (seg == 0 ? 0.0 : __ldcg(gc)) + g;
+        if (lane == 0 && c.slice == 0) *gc = (seg == 0 ? 0.0 : __ldcg(gc)) + g;
       }
     }
     publish_segment_rs(c, a.progress + item, seg);

@@ -170,6 +170,13 @@ void launch_forward_fast_rs_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   launch_sweep(h, kernel, L, d, a);
 }
 template <int M, int NC, int RS>
+void launch_forward_forced_fast_rs_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {  // forced solves on the groups
+  auto kernel = k_forward_fast<2, M, NC, false, true, false, RS>;
+  FastCfg L = plan_fast(h, kernel, fast_fixed_doubles<2, M, NC, false, RS>(d.N2), 2, (size_t)a.B * d.ncol, 0, d.N2, RS, group_doubles<2, RS>());
+  ensure_krylov_fast(h, L, 2, d.N2, a);
+  launch_sweep(h, kernel, L, d, a);
+}
+template <int M, int NC, int RS>
 void launch_backward_fast_rs_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   auto kernel = k_backward_fast<2, M, NC, false, false, RS>;
   FastCfg L = plan_fast(h, kernel, fast_fixed_doubles<2, M, NC, false, RS>(d.N2), 2, (size_t)a.B * d.ncol, 0, d.N2, RS, group_doubles<2, RS>());
@@ -273,6 +280,14 @@ void launch_backward_fast_team_t(qgd_handle* h, QgdDevProb d, SweepArgs a) {
   bool launch_terminal_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                          \
     QGD_FAST_CASE_RS(terminal, M, 2, 2) QGD_FAST_CASE_RS(terminal, M, 3, 2) QGD_FAST_CASE_RS(terminal, M, 2, 4)               \
     QGD_FAST_CASE_RS(terminal, M, 3, 4) QGD_FAST_CASE_RS(terminal, M, 4, 2) QGD_FAST_CASE_RS(terminal, M, 4, 4) return false; \
+  }
+
+// The forced forward solves on the row-split groups, again in translation units of their own (qgd_fast_rf_m<m>.o).
+#define QGD_DEFINE_FAST_LAUNCHERS_RS_FORCED(M)                                                                              \
+  bool launch_forward_fast_forced_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc) {                    \
+    QGD_FAST_CASE_RS(forward_forced, M, 2, 2) QGD_FAST_CASE_RS(forward_forced, M, 3, 2) QGD_FAST_CASE_RS(forward_forced, M, 4, 2) \
+    QGD_FAST_CASE_RS(forward_forced, M, 2, 4) QGD_FAST_CASE_RS(forward_forced, M, 3, 4) QGD_FAST_CASE_RS(forward_forced, M, 4, 4) \
+    return false;                                                                                                           \
   }
 
 // The latency team (four warps per column) in translation units of its own.

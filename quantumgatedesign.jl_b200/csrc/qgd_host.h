@@ -145,7 +145,8 @@ QGD_DECLARE_LAUNCHERS(8)
   bool launch_backward_fast_team_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int el, int nc);               \
   bool launch_forward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc);                  \
   bool launch_backward_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc);                 \
-  bool launch_terminal_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc);
+  bool launch_terminal_fast_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc);                 \
+  bool launch_forward_fast_forced_rs_m##M(qgd_handle* h, QgdDevProb d, qgd::SweepArgs a, int rs, int nc);
 QGD_DECLARE_FAST_LAUNCHERS(1)
 QGD_DECLARE_FAST_LAUNCHERS(2)
 QGD_DECLARE_FAST_LAUNCHERS(3)

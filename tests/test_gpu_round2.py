@@ -746,17 +746,34 @@ def test_row_split_sweeps_identity_preconditioner_lambda_history_and_save_every(
     h.close()
 
 
-def test_forced_gradient_on_a_row_split_problem_runs_on_the_generic_kernels(q, O):
-    """eval_grad_forced at N = 80: the forward sweep that leaves the history takes the row-split groups, the P x nic forced
-    solves the generic kernels (forced sweeps exist for one-warp columns only); equal to the oracle's forced gradient."""
-    prob, controls, U0 = _dispersive(q, (5, 4, 4), 4)
+@pytest.mark.parametrize("sizes,order", [((5, 4, 4), 4), ((6, 5, 5), 6)])
+def test_forced_gradient_and_explicit_forcing_on_row_split_problems(q, O, sizes, order):
+    """eval_grad_forced at N = 80 (two warps per column) and N = 150 (four): the unforced forward sweep AND the P x nic forced
+    solves run on the register-operator sweeps (the forcing formed on the fly from the history, the guard-penalty derivative
+    reduced over the group); equal to the oracle's forced gradient and to the generic kernels'.  eval_forward!(...; forcing)
+    with an explicit forcing array likewise."""
+    prob, controls, U0 = _dispersive(q, sizes, 4)
     P = q.get_number_of_control_parameters(controls)
     pcof = q.configs.cnot3_pcof(P, 5)
-    gf = q.eval_grad_forced(prob, controls, pcof, U0, order=4)
-    st = q.get_handle(prob, controls).stats()
-    assert st["fast_path_launches"] == 1, st   # the unforced forward sweep only
-    ref = O.eval_grad_forced(prob, controls, pcof, U0, order=4)
+    gf = q.eval_grad_forced(prob, controls, pcof, U0, order=order)
+    h = q.get_handle(prob, controls)
+    assert h.stats()["fast_path_launches"] == 2, h.stats()
+    ref = O.eval_grad_forced(prob, controls, pcof, U0, order=order)
     assert rel(gf, ref) < RTOL
+    h.set_option(q.backend.OPT_DISABLE_FAST, 1)
+    gg = q.eval_grad_forced(prob, controls, pcof, U0, order=order)
+    h.set_option(q.backend.OPT_DISABLE_FAST, 0)
+    assert rel(gf, gg) < RTOL
+    rng = np.random.default_rng(11)
+    m = order // 2
+    forcing = np.asfortranarray(1e-2 * rng.standard_normal((prob.real_system_size, m, prob.nsteps + 1, prob.N_initial_conditions)))
+    f0 = h.stats()["fast_path_launches"]
+    fast = h.eval_forward(pcof, order=order, forcing=forcing)
+    assert h.stats()["fast_path_launches"] - f0 == 1
+    h.set_option(q.backend.OPT_DISABLE_FAST, 1)
+    gen = h.eval_forward(pcof, order=order, forcing=forcing)
+    h.set_option(q.backend.OPT_DISABLE_FAST, 0)
+    assert rel(fast["history"], gen["history"]) < RTOL
     q.backend.clear_handles()
 
 
