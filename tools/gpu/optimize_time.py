@@ -6,10 +6,16 @@ sys.path.insert(0, ".")
 import __graft_entry__ as g
 q = g.load_package()
 prob, controls, pcof, target, order = q.configs.cnot3(nsteps=550, tf=550.0, gmres_tol=1e-12)
+# cold start of the process: library load (CUDA registers the fat binaries of every kernel instantiation), context, handle,
+# first launches of each kernel -- timed on its own with one optimiser iteration
+t0 = time.perf_counter()
+q.optimize_gate(prob, controls, pcof, target, order=order, maxIter=1, ridge_penalty_strength=1e-2)
+cold = time.perf_counter() - t0
 t0 = time.perf_counter()
 res = q.optimize_gate(prob, controls, pcof, target, order=order, maxIter=10, ridge_penalty_strength=1e-2)
 dt = time.perf_counter() - t0
 print(json.dumps({"workload": "optimize_gate, C2 CNOT3 order 8, 550 steps, 10 L-BFGS-B iterations (scipy; the reference uses Ipopt)",
                   "seconds": dt, "iterations": res["iterations"], "forward_solves": res["n_forward_solves"], "adjoint_solves": res["n_adjoint_solves"],
                   "histories_reused_on_device": res["n_history_reused"], "objective": [res["initial_objective"], res["final_objective"]],
-                  "infidelity": res["final_infidelity"], "seconds_per_iteration": dt / max(res["iterations"], 1)}))
+                  "infidelity": res["final_infidelity"], "seconds_per_iteration": dt / max(res["iterations"], 1),
+                  "cold_start_seconds_one_iteration": cold}))
