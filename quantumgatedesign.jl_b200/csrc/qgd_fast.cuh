@@ -91,8 +91,11 @@ __device__ __forceinline__ double warp_allsum(double p) {
 #endif
 }
 
+// 1: one FMA chain per local dot product (2 EL instructions) instead of two chains and an add (2 EL + 1).  MEASURED ON B200 (round 2,
+// A/B through tools/build_variant.sh on the final library): adjoint sweep 812 -> 794 ms at batch 592, forward sweep unchanged
+// (701 ms), 389.7 -> 394.5 evals/s; every GPU parity test unchanged (same GMRES iteration counts).  On.
 #ifndef QGD_DOT_CHAIN
-#define QGD_DOT_CHAIN 0  // 1: one FMA chain per dot product (2 EL instructions) instead of two chains and an add (2 EL + 1)
+#define QGD_DOT_CHAIN 1
 #endif
 template <int EL>
 __device__ __forceinline__ double vdot_local(const Vec<EL>& a, const Vec<EL>& b) {
